@@ -1,0 +1,119 @@
+// Shared host/device helpers of libpangenie_b200 (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pangenie_b200.h"
+
+namespace pg {
+
+int fail(int code, const std::string& msg);  // records the thread-local error string, returns code
+void clear_error();
+int last_code();  // status code of the last fail() on this thread
+
+#define PG_CUDA(call)                                                                           \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return pg::fail(PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+#define PG_TRY(call)              \
+  do {                            \
+    int st_ = (call);             \
+    if (st_ != PG_OK) return st_; \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int d) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(d);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+/** Owning device allocation (freed on destruction); grows on demand, never shrinks. */
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  int reserve(size_t n) {
+    if (n <= cap) return PG_OK;
+    release();
+    if (n == 0) return PG_OK;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(PG_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(n * sizeof(T)) + " B): " + cudaGetErrorString(e));
+    }
+    cap = n;
+    return PG_OK;
+  }
+};
+
+/** Verifies that `device` exists and is a Blackwell-class (sm_100+) part. */
+int check_device(int device);
+
+/** Counts kernel launches per host thread so pg_timings.kernel_launches is a measured number. */
+extern thread_local uint64_t g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches += n; }
+
+// ---- 2-bit k-mer arithmetic shared by the counting and the lookup kernels -------------------------
+__host__ __device__ inline uint64_t kmer_mask(uint32_t k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL); }
+
+__device__ __forceinline__ uint64_t revcomp_2bit(uint64_t x, uint32_t k) {
+  // complement every base (3 - c == ~c & 3), reverse the order of the 2-bit groups
+  uint64_t y = __brevll(~x);
+  y = ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
+  return y >> (64 - 2 * k);
+}
+
+__device__ __forceinline__ uint64_t hash_kmer(uint64_t h) {
+  h ^= h >> 33;
+  h *= 0xff51afd7ed558ccdULL;
+  h ^= h >> 33;
+  h *= 0xc4ceb9fe1a85ec53ULL;
+  h ^= h >> 33;
+  return h;
+}
+
+constexpr uint64_t EMPTY_KEY = ~0ULL;  // never a canonical k-mer for k <= 32 (all-T canonicalises to all-A)
+
+}  // namespace pg
+
+/** Device k-mer table + streaming state (definition shared by kmer_count.cu and pipeline.cu). */
+struct pg_counter {
+  int device = 0;
+  uint32_t k = 0;
+  uint64_t capacity = 0;      // slots
+  uint64_t max_distinct = 0;  // keys the caller asked room for
+  uint64_t* keys = nullptr;   // [capacity] canonical k-mer or EMPTY_KEY
+  uint32_t* counts = nullptr; // [capacity]
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  // streaming scratch
+  char* d_stage[2] = {nullptr, nullptr};
+  char* h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};   // kernel finished reading d_stage[i]
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr};  // H2D into d_stage[i] finished
+  uint32_t* d_tile_meta = nullptr;                  // per-tile scan scratch
+  size_t tile_meta_cap = 0;
+  unsigned long long* d_scalars = nullptr;          // [0]=distinct, [1]=error flags, [2]=carry state, [3]=kmers seen
+  uint64_t kmers_seen = 0;
+  double last_feed_ms = 0.0;
+};

@@ -1,0 +1,467 @@
+// Forward-backward kernels over diploid haplotype-pair states (replaces src/hmm.cpp:175-405,
+// src/transitionprobabilitycomputer.cpp:8-39 and the per-cell ColumnIndexer lookups of the reference).
+//
+// Recurrence (per HMM column t, P selected paths, state matrix X is P x P):
+//   forward : F_t = e'_t o trans_t(F_{t-1})          F_0 = e'_0
+//   backward: Y_t = e'_t o pre_t,  pre_t = trans_{t+1}(Y_{t+1}),  pre_{C-1} = 1
+//   trans(X)_{ij} = a X_ij + b (R_i + R_j) + c T,   R = row sums of X, T = total,
+//   a = e^{-2x}, b = r e^{-x}, c = r^2 with x = d/P, r = (1-e^{-x})/P  (== t0-2t1+t2, t1-t2, t2 of
+//   src/transitionprobabilitycomputer.cpp:14-18; the reference's column sums equal the row sums because
+//   X stays symmetric)
+//   posterior_t(g) = sum_{cells in genotype g} F_t o pre_t                       (hmm.cpp:362-368)
+// Every column is rescaled by an exact power of two taken from the exponent of the previous total (the
+// reference divides by the total, hmm.cpp:253-267; any per-column scale cancels in the per-variant
+// normalisation, and the un-normalised reference scale is reconstructed in finalize_kernel).
+// Underflow fallbacks follow hmm.cpp:258-260 / :377-379: a zero total replaces the column by uniform.
+//
+// Decomposition (DESIGN.md "HMM schedule"):
+//   phase 1 "skeleton": one CTA per (chromosome, direction) walks the whole chain, state in registers,
+//            storing a checkpoint every B columns.  Latency bound (one barrier + two reductions per column).
+//   phase 2 "blocks":   every block of B columns is independent given its two checkpoints; a CTA recomputes
+//            forward (storing F_t: 8 P^2 bytes per column), then backward fusing the posterior (reading F_t
+//            back).  All SMs busy: this is the HBM-bound kernel the roofline is reported for.
+#pragma once
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int HMM_PMAX = 256;       // largest number of selected paths supported
+constexpr int HMM_RS_PAD = 288;     // row-sum array length in shared memory
+constexpr int HMM_NSLOT = 6;        // descriptor ring slots
+constexpr int HMM_PREFETCH = 4;     // descriptor prefetch distance (columns)
+constexpr int HMM_FAST_A = 4;       // columns with <= 4 alleles: staged emission table + class sums
+constexpr int HMM_BMAX = 256;       // largest block length
+
+// Per-column descriptor record, contiguous in HBM so one cp.async burst fetches it.
+// doubles: [0..3] a,b,c,kappa of the transition (t-1 -> t); [4..7] the same for (t -> t+1);
+//          [8] header: u32 A (alleles), u32 variant index; [9] emission pointer (u64, A > HMM_FAST_A);
+//          [10..25] 4x4 emission table (row-major, allele-index space) when A <= HMM_FAST_A;
+// then u16 aidx[P] (allele index of each selected path), padded to 16 bytes.
+constexpr int DESC_HEAD_DOUBLES = 26;
+__host__ __device__ inline size_t desc_bytes(uint32_t P) { return (size_t)DESC_HEAD_DOUBLES * 8 + (((size_t)P * 2 + 15) & ~(size_t)15); }
+constexpr int DESC_SLOT_WORDS = (DESC_HEAD_DOUBLES * 8 + 2 * HMM_PMAX + 16) / 8;
+
+struct ChromCols {
+  uint32_t col_begin;  // first global column index of the chromosome
+  uint32_t col_end;    // one past the last
+  uint32_t blk_begin;  // first global block index of the chromosome
+  uint32_t n_blocks;
+};
+
+struct ChainParams {
+  uint32_t P;                  // selected paths
+  uint32_t B;                  // block length (columns)
+  const uint8_t* desc;         // [n_cols] descriptor records
+  uint32_t desc_stride;
+  const ChromCols* chroms;     // [n_chrom]
+  double* ckpt_fwd;            // [n_blocks_total][P*P]  F of the column before block k (valid for k >= 1 in a chrom)
+  double* ckpt_bwd;            // [n_blocks_total][P*P]  Y of the column after block k (valid for k < n_blocks-1)
+  double* tot_fwd;             // [n_cols] TF_t = sum F_t
+  double* tot_bwd;             // [n_cols] TY_t = sum Y_t
+  double* block_buf;           // [grid][B][P*P] forward columns of the block being processed
+  double* post;                // VCF-ordered raw posteriors (zero-initialised)
+  const uint64_t* gl_off;      // [n_variants+1]
+  const uint32_t* allele_off;  // [n_variants+1]
+  const uint16_t* allele_ids;  // [A_total]
+  uint32_t* work_counter;      // phase-2 job queue head
+  const uint2* jobs;           // [n_jobs] (chromosome, block)
+  uint32_t n_jobs;
+};
+
+__device__ __forceinline__ double pow2_scale_of(double T) {
+  // exact 2^-(unbiased exponent of T) for T > 0
+  const int e = (__double2hiint(T) >> 20) & 0x7ff;
+  return __hiloint2double((2046 - e) << 20, 0);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+__device__ __forceinline__ uint32_t pair_index(uint32_t a, uint32_t b) {  // VCF order (genotypingresult.cpp:61)
+  const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+  return hi * (hi + 1) / 2 + lo;
+}
+
+struct ChainSmem {
+  double rs[2][HMM_RS_PAD];              // row sums of the current / next state
+  double wr[2][HMM_FAST_A][HMM_RS_PAD];  // per-row, per-column-class sums of F o pre, double-buffered
+  uint8_t wr_ai[2][HMM_RS_PAD];          // allele index of each row for the column held in wr[.]
+  double tf[HMM_BMAX];                   // forward totals of the block's columns (phase 2)
+  unsigned long long desc[HMM_NSLOT][DESC_SLOT_WORDS];
+};
+
+// =================================================================================================
+// Register-resident chain.  L lanes per row, CPL columns per lane (interleaved: col = lc + s*L),
+// RPW rows per thread, G = 32/L rows per warp pass; warp w owns rows [w*RPW*G, (w+1)*RPW*G).
+// =================================================================================================
+template <int L, int CPL, int RPW>
+struct Chain {
+  static constexpr int G = 32 / L;
+  double x[RPW][CPL];
+  double rrow[RPW];
+  int w, lane, lr, lc;
+  int P;
+  ChainSmem* sm;
+  const ChainParams* prm;
+  // posterior plumbing of the column being processed (multi-allelic general path)
+  double* post_col;
+  const uint16_t* ids_col;
+
+  __device__ __forceinline__ int row(int r) const { return (w * RPW + r) * G + lr; }
+  __device__ __forceinline__ int col(int s) const { return lc + s * L; }
+
+  __device__ __forceinline__ void init(ChainSmem* s, const ChainParams* p) {
+    sm = s;
+    prm = p;
+    P = (int)p->P;
+    w = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    lr = lane / L;
+    lc = lane % L;
+    post_col = nullptr;
+    ids_col = nullptr;
+  }
+
+  __device__ __forceinline__ double row_reduce(double v) const {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+
+  // total of the row sums in rs[buf]; every warp evaluates the same expression -> bitwise identical T
+  __device__ __forceinline__ double total(int buf) const {
+    double t = 0.0;
+    for (int i = lane; i < P; i += 32) t += sm->rs[buf][i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  }
+
+  // ---- descriptor ring: exactly one cp.async group per call, issued in column order ---------------
+  __device__ __forceinline__ void prefetch_desc(long long t, long long lo, long long hi) const {
+    if (t >= lo && t < hi) {
+      const uint8_t* src = prm->desc + (size_t)t * prm->desc_stride;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(sm->desc[(unsigned long long)t % HMM_NSLOT]);
+      for (uint32_t o = threadIdx.x * 16; o < prm->desc_stride; o += blockDim.x * 16) cp_async16(dst + o, src + o);
+    }
+    cp_async_commit();
+  }
+  __device__ __forceinline__ const double* desc_d(long long t) const {
+    return reinterpret_cast<const double*>(sm->desc[(unsigned long long)t % HMM_NSLOT]);
+  }
+
+  // ---- state I/O (dense row-major P x P doubles; each thread always touches the same cells) -------
+  __device__ __forceinline__ void store_state(double* dst) const {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = row(r);
+      if (i < P) {
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+          const int j = col(s);
+          if (j < P) dst[(size_t)i * P + j] = x[r][s];
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void load_state(const double* src) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = row(r);
+#pragma unroll
+      for (int s = 0; s < CPL; ++s) {
+        const int j = col(s);
+        x[r][s] = (i < P && j < P) ? src[(size_t)i * P + j] : 0.0;
+      }
+    }
+  }
+  // publish the row sums of x into rs[buf]; caller must __syncthreads() before anyone reads them
+  __device__ __forceinline__ void publish_rowsums(int buf) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < CPL; ++s) acc += x[r][s];
+      acc = row_reduce(acc);
+      rrow[r] = acc;
+      if (lc == 0 && row(r) < P) sm->rs[buf][row(r)] = acc;
+    }
+  }
+
+  __device__ __forceinline__ double emission(const double* d, uint32_t A, uint32_t ai, uint32_t aj) const {
+    if (A <= HMM_FAST_A) return d[10 + ai * HMM_FAST_A + aj];
+    const double* g = reinterpret_cast<const double*>(*reinterpret_cast<const unsigned long long*>(d + 9));
+    return __ldg(g + (size_t)ai * A + aj);
+  }
+
+  __device__ __forceinline__ void bind_posterior(const double* d) {
+    const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
+    post_col = prm->post + prm->gl_off[v];
+    ids_col = prm->allele_ids + prm->allele_off[v];
+  }
+
+  // ---- one column.  FIRST: no transition (pre = 1).  WITH_POST: accumulate F o pre.  -----------------
+  // Reads rs[cbuf] (row sums of x), writes rs[nbuf]; coefficients (t-1 -> t) forward, (t -> t+1) backward.
+  template <bool BACKWARD, bool FIRST, bool WITH_POST>
+  __device__ __forceinline__ void step(long long t, int cbuf, int nbuf, double Tprev, const double* ucol,
+                                       bool u_dead, int wbuf) {
+    const double* d = desc_d(t);
+    const uint16_t* aidx = reinterpret_cast<const uint16_t*>(d + DESC_HEAD_DOUBLES);
+    const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
+    const double S = (double)P * (double)P;
+    const bool dead = !FIRST && !(Tprev > 0.0);  // previous column underflowed -> uniform replacement
+    double ca = 0.0, cb = 0.0, cc = 1.0;
+    if (!FIRST) {
+      const int o = BACKWARD ? 4 : 0;
+      if (!dead) {
+        const double sc = pow2_scale_of(Tprev);
+        ca = d[o] * sc;
+        cb = d[o + 1] * sc;
+        cc = d[o + 2] * Tprev * sc;
+      } else {
+        cc = BACKWARD ? 1.0 / S : d[o + 3] / S;
+      }
+    }
+    const bool fastA = A <= HMM_FAST_A;
+    if (WITH_POST && !fastA) bind_posterior(d);
+    const double uni = 1.0 / S;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = row(r);
+      const uint32_t ai = i < P ? aidx[i] : 0;
+      const double rho = FIRST ? 1.0 : cb * rrow[r] + cc;
+      double acc = 0.0;
+      double wc[HMM_FAST_A];
+#pragma unroll
+      for (int q = 0; q < HMM_FAST_A; ++q) wc[q] = 0.0;
+#pragma unroll
+      for (int s = 0; s < CPL; ++s) {
+        const int j = col(s);
+        const bool ok = i < P && j < P;
+        const uint32_t aj = j < P ? aidx[j] : 0;
+        const double pre = FIRST ? 1.0 : fma(ca, x[r][s], rho + (j < P ? cb * sm->rs[cbuf][j] : 0.0));
+        if (WITH_POST) {
+          // the reference's backward cells of a dead column are all zero (hmm.cpp:348-352 with zero helpers)
+          double uu = 0.0;
+          if (ok) uu = u_dead ? uni : ucol[(size_t)i * P + j];
+          const double wv = (ok && !dead) ? uu * pre : 0.0;
+          if (fastA) {
+#pragma unroll
+            for (int q = 0; q < HMM_FAST_A; ++q) wc[q] += (aj == (uint32_t)q) ? wv : 0.0;
+          } else if (wv != 0.0) {
+            atomicAdd(post_col + pair_index(ids_col[ai], ids_col[aj]), wv);  // rare general path
+          }
+        }
+        const double v = ok ? pre * emission(d, A, ai, aj) : 0.0;
+        x[r][s] = v;
+        acc += v;
+      }
+      acc = row_reduce(acc);
+      rrow[r] = acc;
+      if (lc == 0 && i < P) sm->rs[nbuf][i] = acc;
+      if (WITH_POST && fastA) {
+#pragma unroll
+        for (int q = 0; q < HMM_FAST_A; ++q) {
+          const double c = row_reduce(wc[q]);
+          if (lc == 0 && i < P) sm->wr[wbuf][q][i] = c;
+        }
+        if (lc == 0 && i < P) sm->wr_ai[wbuf][i] = (uint8_t)ai;
+      }
+    }
+  }
+
+  // ---- posterior writer for a fast-A column whose class sums sit in wr[wbuf] (call after the barrier) ----
+  // One warp: lane (alpha, beta) = (lane/4, lane%4) sums wr[beta][i] over rows i with allele index alpha.
+  __device__ __forceinline__ void write_posterior(long long t, int wbuf) {
+    const double* d = desc_d(t);
+    const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
+    if (A > HMM_FAST_A) return;
+    const uint32_t alpha = lane >> 2, beta = lane & 3;
+    double m = 0.0;
+    if (lane < 16 && alpha < A && beta < A)
+      for (int i = 0; i < P; ++i) m += (sm->wr_ai[wbuf][i] == alpha) ? sm->wr[wbuf][beta][i] : 0.0;
+    const double mt = __shfl_sync(0xffffffffu, m, (beta << 2) | alpha);  // M[beta][alpha]
+    if (lane < 16 && alpha <= beta && beta < A) {
+      const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
+      const uint16_t* ids = prm->allele_ids + prm->allele_off[v];
+      const double val = alpha == beta ? m : m + mt;
+      prm->post[prm->gl_off[v] + pair_index(ids[alpha], ids[beta])] = val;
+    }
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
+// phase 1: skeleton chains.  grid = (n_chrom, 2): y = 0 forward, y = 1 backward.
+// -------------------------------------------------------------------------------------------------
+template <int L, int CPL, int RPW, int NT>
+__global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
+  Chain<L, CPL, RPW> ch;
+  ch.init(sm, &p);
+  const ChromCols cc = p.chroms[blockIdx.x];
+  const long long c0 = cc.col_begin, c1 = cc.col_end;
+  if (cc.n_blocks <= 1) return;
+  const long long B = p.B;
+  const size_t PP = (size_t)p.P * p.P;
+  constexpr int D = HMM_PREFETCH;
+  int cur = 0;
+  if (blockIdx.y == 0) {
+    // forward: needs F at columns c0 + k*B - 1 for k = 1 .. n_blocks-1
+    const long long last = c0 + (long long)(cc.n_blocks - 1) * B - 1;
+    for (int d = 0; d < D; ++d) ch.prefetch_desc(c0 + d, c0, c1);
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    ch.template step<false, true, false>(c0, 0, 0, 0.0, nullptr, false, 0);
+    ch.prefetch_desc(c0 + D, c0, c1);
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    for (long long t = c0 + 1; t <= last; ++t) {
+      if ((t - c0) % B == 0) ch.store_state(p.ckpt_fwd + (size_t)(cc.blk_begin + (t - c0) / B) * PP);
+      const double T = ch.total(cur);
+      ch.template step<false, false, false>(t, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.prefetch_desc(t + D, c0, c1);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      cur ^= 1;
+    }
+    ch.store_state(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * PP);
+  } else {
+    // backward: needs Y at columns c0 + k*B for k = 1 .. n_blocks-1 (stored as ckpt_bwd[k-1])
+    const long long first = c0 + B;
+    for (int d = 0; d < D; ++d) ch.prefetch_desc(c1 - 1 - d, c0, c1);
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    ch.template step<true, true, false>(c1 - 1, 0, 0, 0.0, nullptr, false, 0);
+    if ((c1 - 1 - c0) % B == 0) ch.store_state(p.ckpt_bwd + (size_t)(cc.blk_begin + (c1 - 1 - c0) / B - 1) * PP);
+    ch.prefetch_desc(c1 - 1 - D, c0, c1);
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    for (long long t = c1 - 2; t >= first; --t) {
+      const double T = ch.total(cur);
+      ch.template step<true, false, false>(t, cur, cur ^ 1, T, nullptr, false, 0);
+      if ((t - c0) % B == 0) ch.store_state(p.ckpt_bwd + (size_t)(cc.blk_begin + (t - c0) / B - 1) * PP);
+      ch.prefetch_desc(t - D, c0, c1);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// phase 2: block forward-backward with fused posterior.  Persistent CTAs pull (chromosome, block) jobs.
+// -------------------------------------------------------------------------------------------------
+template <int L, int CPL, int RPW, int NT>
+__global__ void __launch_bounds__(NT) block_kernel(const ChainParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
+  __shared__ uint32_t s_job;
+  Chain<L, CPL, RPW> ch;
+  ch.init(sm, &p);
+  const size_t PP = (size_t)p.P * p.P;
+  double* buf = p.block_buf + (size_t)blockIdx.x * p.B * PP;
+  constexpr int D = HMM_PREFETCH;
+  const int NW = NT / 32;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_job = atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    const uint32_t job = s_job;
+    if (job >= p.n_jobs) break;
+    const uint2 jb = p.jobs[job];
+    const ChromCols cc = p.chroms[jb.x];
+    const long long c0 = cc.col_begin, c1 = cc.col_end;
+    const long long cb = c0 + (long long)jb.y * p.B;
+    const long long ce = (cb + p.B < c1) ? cb + p.B : c1;
+    const uint32_t gblk = cc.blk_begin + jb.y;
+    int cur = 0;
+
+    // ---------------- forward sub-pass: F_t for t in [cb, ce) -> buf ----------------
+    for (int d = 0; d < D; ++d) ch.prefetch_desc(cb + d, cb, ce);
+    long long t = cb;
+    if (jb.y == 0) {
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      ch.template step<false, true, false>(cb, 0, 0, 0.0, nullptr, false, 0);
+      ch.store_state(buf);
+      ch.prefetch_desc(cb + D, cb, ce);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      t = cb + 1;
+    } else {
+      ch.load_state(p.ckpt_fwd + (size_t)gblk * PP);
+      ch.publish_rowsums(0);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+    }
+    for (; t < ce; ++t) {
+      const double T = ch.total(cur);
+      if (threadIdx.x == 0 && t > cb) sm->tf[t - 1 - cb] = T;
+      ch.template step<false, false, false>(t, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.store_state(buf + (size_t)(t - cb) * PP);
+      ch.prefetch_desc(t + D, cb, ce);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      cur ^= 1;
+    }
+    {
+      const double T = ch.total(cur);
+      if (threadIdx.x == 0) sm->tf[ce - 1 - cb] = T;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    for (long long q = cb + threadIdx.x; q < ce; q += NT) p.tot_fwd[q] = sm->tf[q - cb];
+
+    // ---------------- backward sub-pass with posterior ----------------
+    for (int d = 0; d < D; ++d) ch.prefetch_desc(ce - 1 - d, cb, ce);
+    cur = 0;
+    t = ce - 1;
+    long long pending = -1;  // column whose class sums await the posterior writer
+    if (ce == c1) {
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      ch.template step<true, true, true>(t, 0, 0, 0.0, buf + (size_t)(t - cb) * PP, !(sm->tf[t - cb] > 0.0), (int)(t & 1));
+      ch.prefetch_desc(t - D, cb, ce);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      pending = t;
+      --t;
+    } else {
+      ch.load_state(p.ckpt_bwd + (size_t)gblk * PP);
+      ch.publish_rowsums(0);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+    }
+    for (; t >= cb; --t) {
+      if (pending >= 0 && ch.w == (int)(pending % NW)) ch.write_posterior(pending, (int)(pending & 1));
+      const double T = ch.total(cur);
+      if (threadIdx.x == 0 && t + 1 < c1) p.tot_bwd[t + 1] = T;
+      if (t - 2 >= cb) {  // pull the forward column needed two steps from now towards L2
+        const char* nxt = reinterpret_cast<const char*>(buf + (size_t)(t - 2 - cb) * PP);
+        for (size_t o = (size_t)threadIdx.x * 128; o < PP * 8; o += (size_t)NT * 128) prefetch_l2(nxt + o);
+      }
+      ch.template step<true, false, true>(t, cur, cur ^ 1, T, buf + (size_t)(t - cb) * PP, !(sm->tf[t - cb] > 0.0), (int)(t & 1));
+      ch.prefetch_desc(t - D, cb, ce);
+      cp_async_wait<D - 1>();
+      __syncthreads();
+      cur ^= 1;
+      pending = t;
+    }
+    if (pending >= 0 && ch.w == (int)(pending % NW)) ch.write_posterior(pending, (int)(pending & 1));
+    {
+      const double T = ch.total(cur);
+      if (threadIdx.x == 0) p.tot_bwd[cb] = T;
+    }
+    cp_async_wait<0>();
+  }
+}
+
+}  // namespace pg

@@ -1,0 +1,910 @@
+// K-mer counting on the device: replaces the jellyfish-backed JellyfishCounter of the reference
+// (src/jellyfishcounter.hpp:46-68 COUNT/PRIME/UPDATE, src/jellyfishcounter.cpp:26-153).
+//
+// Data layout in HBM
+//   keys  [capacity] u64  canonical 2-bit k-mer (first base most significant) or EMPTY_KEY
+//   counts[capacity] u32  occurrences (jellyfish's counters are effectively unbounded; u32 here)
+//   open addressing, linear probing, home slot = mulhi64(mix64(kmer), capacity), load <= 0.6.
+//
+// Text pipeline (per chunk of the read/segment file resident in HBM), all on one stream:
+//   tile_lines_kernel   newline count + last-newline position per 8064-byte tile   (streams the text once)
+//   tile_scan_kernel    exclusive scan over tiles -> line phase / header state at each tile start + carry
+//   count_tile_kernel   per tile: 128-bit loads -> per-byte line classification (block scan) -> compaction of
+//                       sequence symbols into shared memory -> rolling canonical k-mers (16 per thread) ->
+//                       hash probes, 4 independent loads in flight per thread, warp-aggregated atomics.
+// Algorithmic bytes: text bytes + 16 B per k-mer (8 B key probe + RMW of the count sector).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int CT_THREADS = 512;                       // threads per counting CTA
+constexpr int CT_TILE = CT_THREADS * 16;              // bytes loaded per tile (one uint4 per thread)
+constexpr int CT_HALO = 128;                          // look-ahead so k-mers may span tiles / chunks
+constexpr int CT_ADV = CT_TILE - CT_HALO;             // tile advance (multiple of 16)
+constexpr uint64_t CHUNK_BYTES = 64ull << 20;         // streaming chunk (multiple of 16)
+constexpr int SYM_PAD = 64;
+
+// scalars[] slots
+enum { SC_DISTINCT = 0, SC_ERROR = 1, SC_CARRY = 2, SC_KMERS = 3, SC_COUNT_SUM = 4, SC_N = 8 };
+// error bits
+enum { ERR_PROBE = 1, ERR_HALO = 2 };
+// FASTA line state
+enum { LS_LINE_START = 0, LS_HEADER = 1, LS_SEQ = 2 };
+
+__device__ __forceinline__ uint32_t base_code(uint32_t c) {
+  // A/a=0 C/c=1 G/g=2 T/t=3, anything else 4 (jellyfish mer_dna::code)
+  c &= 0xDFu;  // fold case
+  return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: per-tile newline statistics over the OWNED bytes [t*ADV, min((t+1)*ADV, n))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_lines_kernel(const char* __restrict__ text, uint64_t n,
+                                                          uint32_t* __restrict__ nl_count,
+                                                          int64_t* __restrict__ last_nl) {
+  const uint64_t base = (uint64_t)blockIdx.x * CT_ADV;
+  const uint64_t end = min(base + (uint64_t)CT_ADV, n);
+  uint32_t cnt = 0;
+  long long last = -1;
+  for (uint64_t p = base + (uint64_t)threadIdx.x * 16; p < end; p += 256 * 16) {
+    if (p + 16 <= end) {
+      uint4 v = *reinterpret_cast<const uint4*>(text + p);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (((w[i] >> (8 * b)) & 0xff) == '\n') {
+            ++cnt;
+            last = (long long)(p + 4 * i + b);
+          }
+      }
+    } else {
+      for (uint64_t q = p; q < end; ++q)
+        if (text[q] == '\n') {
+          ++cnt;
+          last = (long long)q;
+        }
+    }
+  }
+  __shared__ uint32_t s_cnt[8];
+  __shared__ long long s_last[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_cnt[threadIdx.x >> 5] = cnt;
+    s_last[threadIdx.x >> 5] = last;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    long long l = -1;
+    for (int i = 0; i < 8; ++i) {
+      c += s_cnt[i];
+      l = max(l, s_last[i]);
+    }
+    nl_count[blockIdx.x] = c;
+    last_nl[blockIdx.x] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: one CTA scans the tile statistics -> tile_meta[t] = (line phase mod 4) | (fasta state << 2),
+// and updates the carry for the next chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const char* __restrict__ text, uint64_t n, uint32_t n_tiles,
+                                                          const uint32_t* __restrict__ nl_count,
+                                                          const int64_t* __restrict__ last_nl, int is_fastq,
+                                                          uint32_t* __restrict__ tile_meta,
+                                                          unsigned long long* __restrict__ scalars) {
+  __shared__ uint32_t s_sum[1024];
+  __shared__ long long s_max[1024];
+  const uint32_t carry = (uint32_t)scalars[SC_CARRY];
+  const uint32_t per = (n_tiles + 1023) / 1024;
+  const uint32_t t0 = threadIdx.x * per, t1 = min(t0 + per, n_tiles);
+  uint32_t sum = 0;
+  long long mx = -1;
+  for (uint32_t t = t0; t < t1; ++t) {
+    sum += nl_count[t];
+    mx = max(mx, (long long)last_nl[t]);
+  }
+  s_sum[threadIdx.x] = sum;
+  s_max[threadIdx.x] = mx;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    uint32_t a = 0;
+    long long b = -1;
+    if ((int)threadIdx.x >= o) {
+      a = s_sum[threadIdx.x - o];
+      b = s_max[threadIdx.x - o];
+    }
+    __syncthreads();
+    s_sum[threadIdx.x] += a;
+    s_max[threadIdx.x] = max(s_max[threadIdx.x], b);
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? s_sum[threadIdx.x - 1] : 0;
+  long long runmax = threadIdx.x ? s_max[threadIdx.x - 1] : -1;
+  auto fasta_state_at = [&](long long last_before, uint64_t pos) -> uint32_t {
+    // state of the line containing byte `pos`, given the last newline strictly before pos
+    if (last_before >= 0) {
+      if ((uint64_t)(last_before + 1) == pos) return LS_LINE_START;
+      return text[last_before + 1] == '>' ? LS_HEADER : LS_SEQ;
+    }
+    if (carry == LS_LINE_START) return pos == 0 ? LS_LINE_START : (text[0] == '>' ? LS_HEADER : LS_SEQ);
+    return carry;
+  };
+  for (uint32_t t = t0; t < t1; ++t) {
+    const uint64_t base = (uint64_t)t * CT_ADV;
+    uint32_t meta = is_fastq ? ((carry + run) & 3u) : (fasta_state_at(runmax, base) << 2);
+    tile_meta[t] = meta;
+    run += nl_count[t];
+    runmax = max(runmax, (long long)last_nl[t]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 1023) {
+    const uint32_t total = s_sum[1023];
+    const long long lastall = s_max[1023];
+    scalars[SC_CARRY] = is_fastq ? ((carry + total) & 3u) : fasta_state_at(lastall, n);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide exclusive scans (512 threads = 16 warps)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exscan_add(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = lane < CT_THREADS / 32 ? s_warp[lane] : 0;
+    uint32_t xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += y;
+    }
+    if (lane < CT_THREADS / 32) s_warp[lane] = xi - x;  // exclusive warp offsets
+    if (lane == 31) s_warp[32] = xi;                      // grand total
+  }
+  __syncthreads();
+  uint32_t r = inc - v + s_warp[w];
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ int block_exscan_max(int v, int* s_warp) {
+  // exclusive prefix maximum (identity -1)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, y);
+  }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = lane < CT_THREADS / 32 ? s_warp[lane] : -1;
+    int xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi = max(xi, y);
+    }
+    int ex = __shfl_up_sync(0xffffffffu, xi, 1);
+    if (lane == 0) ex = -1;
+    if (lane < CT_THREADS / 32) s_warp[lane] = ex;
+  }
+  __syncthreads();
+  int prev_lane = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) prev_lane = -1;
+  int r = max(prev_lane, s_warp[w]);
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// table operations
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ bool resolve_slow(uint64_t kmer, uint64_t& slot, uint64_t* keys, uint64_t cap,
+                                             unsigned long long* scalars, uint32_t& inserted) {
+  // continues probing at `slot` (inclusive); returns true if the key is (now) present at `slot`
+  for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
+    uint64_t cur = keys[slot];
+    if (cur == kmer) return true;
+    if (cur == EMPTY_KEY) {
+      if (OP == PG_OP_UPDATE) return false;
+      unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
+                                          (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
+      if (prev == EMPTY_KEY) {
+        ++inserted;
+        return true;
+      }
+      if (prev == kmer) return true;
+    }
+    slot = slot + 1 == cap ? 0 : slot + 1;
+  }
+  atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 3: classify, compact, roll, probe
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, int is_fastq,
+                  const uint32_t* __restrict__ tile_meta, uint32_t k, uint64_t* __restrict__ keys,
+                  uint32_t* __restrict__ counts, uint64_t cap, unsigned long long* __restrict__ scalars) {
+  __shared__ __align__(16) uint8_t sym[CT_TILE + 2 * SYM_PAD];
+  __shared__ uint32_t s_warp[40];
+  __shared__ int s_warp_i[32];
+
+  const int tid = threadIdx.x;
+  const uint64_t base = (uint64_t)blockIdx.x * CT_ADV;
+  const uint64_t owned_end = min(base + (uint64_t)CT_ADV, n);
+  const uint64_t pos0 = base + (uint64_t)tid * 16;
+  const uint32_t meta = tile_meta[blockIdx.x];
+
+  // ---- 128-bit load of this thread's 16 bytes ('\0' beyond the end: classified as reset) ----
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (pos0 + 16 <= n_avail) {
+    uint4 v = *reinterpret_cast<const uint4*>(text + pos0);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else {
+    for (int i = 0; i < 16; ++i)
+      if (pos0 + i < n_avail) w[i >> 2] |= (uint32_t)(uint8_t)text[pos0 + i] << (8 * (i & 3));
+  }
+
+  // ---- line classification: symbols of my 16 bytes as nibbles (0-3 base, 4 reset) ----
+  uint64_t nib = 0;
+  uint32_t n_emit = 0, n_emit_owned = 0;
+  auto emit = [&](uint32_t s, uint64_t pos) {
+    nib |= (uint64_t)s << (4 * n_emit);
+    ++n_emit;
+    if (pos < owned_end) ++n_emit_owned;
+  };
+  if (is_fastq) {
+    uint32_t my_nl = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (pos0 + i < n_avail && ((w[i >> 2] >> (8 * (i & 3))) & 0xff) == '\n') ++my_nl;
+    uint32_t tot;
+    uint32_t line = (meta & 3u) + block_exscan_add(my_nl, s_warp, &tot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint64_t pos = pos0 + i;
+      const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
+      if (pos >= n_avail) continue;  // past the end of the text: the trailing pad resets the window
+      if (b == '\n') {
+        if ((line & 3u) == 1u) emit(4u, pos);  // end of a sequence line: k-mers never span records
+        ++line;
+      } else if ((line & 3u) == 1u) {
+        emit(base_code(b), pos);
+      }
+    }
+  } else {
+    int my_last = -1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (pos0 + i < n_avail && ((w[i >> 2] >> (8 * (i & 3))) & 0xff) == '\n') my_last = tid * 16 + i;
+    const int last_before = block_exscan_max(my_last, s_warp_i);  // tile-relative index or -1
+    uint32_t state;
+    if (last_before >= 0) {
+      if (last_before + 1 == tid * 16) state = LS_LINE_START;
+      else state = text[base + last_before + 1] == '>' ? LS_HEADER : LS_SEQ;
+    } else {
+      state = (meta >> 2) & 3u;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint64_t pos = pos0 + i;
+      const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
+      if (pos >= n_avail) continue;
+      if (state == LS_LINE_START) state = b == '>' ? LS_HEADER : LS_SEQ;
+      if (b == '\n') {
+        if (state == LS_HEADER) emit(4u, pos);
+        state = LS_LINE_START;
+      } else if (state == LS_SEQ) {
+        emit(base_code(b), pos);
+      }
+    }
+  }
+
+  // ---- compaction into shared memory, shifted so every k-mer END lies at a compile-time offset ----
+  uint32_t tot_packed;
+  const uint32_t off_packed = block_exscan_add(n_emit | (n_emit_owned << 16), s_warp, &tot_packed);
+  const uint32_t my_off = off_packed & 0xffffu;
+  const uint32_t n_syms = tot_packed & 0xffffu, n_owned_syms = tot_packed >> 16;
+  const uint32_t SHIFT = 33u - k;  // symbols are stored at sym[SHIFT + idx]; sym[0..SHIFT) = reset
+  for (uint32_t i = 0; i < n_emit; ++i) sym[SHIFT + my_off + i] = (uint8_t)((nib >> (4 * i)) & 0xf);
+  if ((uint32_t)tid < SHIFT) sym[tid] = 4;  // leading pad
+  if (tid < 64) {                            // trailing pad: reads reach at most n_syms + 47
+    const uint32_t p = SHIFT + n_syms + tid;
+    if (p < CT_TILE + 2 * SYM_PAD) sym[p] = 4;
+  }
+  __syncthreads();
+
+  // halo sufficiency: an open window at the end of the look-ahead means a k-mer may have been cut
+  // (only possible with pathological whitespace); report instead of silently miscounting.
+  if (tid == 0 && owned_end == base + CT_ADV && n_avail > base + CT_TILE && n_syms > 0) {
+    uint32_t after = n_syms - n_owned_syms;
+    if (after < k - 1) {
+      bool open = true;
+      for (uint32_t i = 0; i < after; ++i)
+        if (sym[SHIFT + n_owned_syms + i] > 3) open = false;
+      if (open && n_owned_syms > 0 && sym[SHIFT + n_owned_syms - 1] < 4) atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_HALO);
+    }
+  }
+
+  // ---- rolling canonical k-mers: thread handles START indices [16 tid, 16 tid + 16) ----
+  const uint32_t s0 = (uint32_t)tid * 16;
+  uint64_t can[16];
+  uint32_t valid = 0;
+  if (s0 < n_owned_syms) {
+    const uint4* sp = reinterpret_cast<const uint4*>(sym + s0);
+    uint4 q0 = sp[0], q1 = sp[1], q2 = sp[2];
+    uint32_t sw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    const uint64_t mask = kmer_mask(k);
+    const uint32_t rshift = 2 * (k - 1);
+    uint64_t fwd = 0, rev = 0;
+    uint32_t run = 0;
+#pragma unroll
+    for (int p = 0; p < 48; ++p) {
+      const uint32_t c = (sw[p >> 2] >> (8 * (p & 3))) & 0xff;
+      if (c < 4) {
+        fwd = ((fwd << 2) | c) & mask;
+        rev = (rev >> 2) | ((uint64_t)(3 - c) << rshift);
+        ++run;
+      } else {
+        run = 0;
+      }
+      if (p >= 32) {  // end at shifted index s0+p  <=>  start index s0 + p - 32
+        const int j = p - 32;
+        can[j] = fwd < rev ? fwd : rev;
+        if (run >= k && s0 + j < n_owned_syms) valid |= 1u << j;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) can[j] = 0;
+  }
+
+  // ---- probes: 4 independent key loads in flight per thread, then resolve ----
+  uint32_t inserted = 0;
+#pragma unroll
+  for (int g = 0; g < 16; g += 4) {
+    uint64_t slot[4], key[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      slot[i] = __umul64hi(hash_kmer(can[g + i]), cap);
+      key[i] = ((valid >> (g + i)) & 1u) ? keys[slot[i]] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool v = (valid >> (g + i)) & 1u;
+      bool hit = false;
+      if (v) {
+        if (key[i] == can[g + i]) hit = true;
+        else if (OP == PG_OP_UPDATE && key[i] == EMPTY_KEY) hit = false;
+        else {
+          if (key[i] != EMPTY_KEY) slot[i] = slot[i] + 1 == cap ? 0 : slot[i] + 1;  // occupied by another key
+          hit = resolve_slow<OP>(can[g + i], slot[i], keys, cap, scalars, inserted);
+        }
+      }
+      if (OP != PG_OP_PRIME) {
+        // warp-aggregated increment: lanes hitting the same slot elect one leader
+        const unsigned long long tag = hit ? (unsigned long long)slot[i] : (~0ull - (unsigned)(tid & 31));
+        const unsigned peers = __match_any_sync(0xffffffffu, tag);
+        if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(counts + slot[i], (uint32_t)__popc(peers));
+      }
+    }
+  }
+  // statistics: distinct keys inserted, k-mers processed
+  uint32_t nk = __popc(valid);
+  for (int o = 16; o > 0; o >>= 1) {
+    inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
+    nk += __shfl_xor_sync(0xffffffffu, nk, o);
+  }
+  if ((tid & 31) == 0) {
+    if (inserted) atomicAdd(scalars + SC_DISTINCT, (unsigned long long)inserted);
+    if (nk) atomicAdd(scalars + SC_KMERS, (unsigned long long)nk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lookups, histogram, sums
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, const uint64_t* __restrict__ keys,
+                                                 const uint32_t* __restrict__ counts, uint64_t cap) {
+  const uint64_t rc = revcomp_2bit(code, k);
+  const uint64_t can = code < rc ? code : rc;
+  uint64_t slot = __umul64hi(hash_kmer(can), cap);
+  for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
+    const uint64_t cur = keys[slot];
+    if (cur == can) return counts[slot];
+    if (cur == EMPTY_KEY) return 0;
+    slot = slot + 1 == cap ? 0 : slot + 1;
+  }
+  return 0;
+}
+
+__global__ void lookup_kernel(const uint64_t* __restrict__ codes, uint64_t n, uint32_t k,
+                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t cap,
+                              uint64_t* __restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    out[i] = table_lookup(codes[i], k, keys, counts, cap);
+  }
+}
+
+constexpr uint32_t HIST_SMEM_BINS = 10240;
+__global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restrict__ counts, uint64_t cap,
+                                                        uint64_t max_count, unsigned long long* __restrict__ bins) {
+  __shared__ uint32_t s_bins[HIST_SMEM_BINS];
+  const bool use_smem = max_count < HIST_SMEM_BINS;
+  if (use_smem) {
+    for (uint32_t i = threadIdx.x; i <= max_count; i += blockDim.x) s_bins[i] = 0;
+    __syncthreads();
+  }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < cap; i += stride) {
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (i + 4 <= cap) {
+      uint4 q = *reinterpret_cast<const uint4*>(counts + i);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      for (uint64_t j = i; j < cap; ++j) v[j - i] = counts[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (v[j] > 0 && v[j] <= max_count) {
+        if (use_smem) atomicAdd(&s_bins[v[j]], 1u);
+        else atomicAdd(bins + v[j], 1ull);
+      }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= max_count; i += blockDim.x)
+      if (s_bins[i]) atomicAdd(bins + i, (unsigned long long)s_bins[i]);
+  }
+}
+
+__global__ void __launch_bounds__(512) count_sum_kernel(const uint32_t* __restrict__ counts, uint64_t cap,
+                                                        unsigned long long* __restrict__ scalars) {
+  unsigned long long s = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) s += counts[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(scalars + SC_COUNT_SUM, s);
+}
+
+__global__ void fill_keys_kernel(uint64_t* keys, uint64_t cap) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) keys[i] = EMPTY_KEY;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int ensure_stage(pg_counter* c, bool need_host) {
+  for (int i = 0; i < 2; ++i) {
+    if (!c->d_stage[i]) PG_CUDA(cudaMalloc((void**)&c->d_stage[i], CHUNK_BYTES + 256));
+    if (need_host && !c->h_stage[i]) PG_CUDA(cudaMallocHost((void**)&c->h_stage[i], CHUNK_BYTES + 256));
+  }
+  return PG_OK;
+}
+
+static int ensure_tile_meta(pg_counter* c, size_t n_tiles) {
+  if (n_tiles <= c->tile_meta_cap) return PG_OK;
+  if (c->d_tile_meta) cudaFree(c->d_tile_meta);
+  c->d_tile_meta = nullptr;
+  // layout: [meta u32 x T][nl_count u32 x T][last_nl i64 x T]
+  size_t cap = n_tiles + 1024;
+  PG_CUDA(cudaMalloc((void**)&c->d_tile_meta, cap * 16));
+  c->tile_meta_cap = cap;
+  return PG_OK;
+}
+
+static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t n_avail, int is_fastq, int op) {
+  const uint32_t n_tiles = (uint32_t)((n + CT_ADV - 1) / CT_ADV);
+  if (n_tiles == 0) return PG_OK;
+  PG_TRY(ensure_tile_meta(c, n_tiles));
+  uint32_t* meta = c->d_tile_meta;
+  uint32_t* nlc = meta + c->tile_meta_cap;
+  int64_t* lnl = reinterpret_cast<int64_t*>(meta + 2 * c->tile_meta_cap);
+  tile_lines_kernel<<<n_tiles, 256, 0, c->stream>>>(d_text, n, nlc, lnl);
+  tile_scan_kernel<<<1, 1024, 0, c->stream>>>(d_text, n, n_tiles, nlc, lnl, is_fastq, meta, c->d_scalars);
+  switch (op) {
+    case PG_OP_COUNT:
+      count_tile_kernel<PG_OP_COUNT><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->d_scalars);
+      break;
+    case PG_OP_PRIME:
+      count_tile_kernel<PG_OP_PRIME><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->d_scalars);
+      break;
+    default:
+      count_tile_kernel<PG_OP_UPDATE><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->d_scalars);
+  }
+  count_launch(3);
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
+static int feed_impl(pg_counter* c, const char* src, uint64_t len, int op) {
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  if (op < 0 || op > 2) return fail(PG_ERR_ARG, "invalid op");
+  if (len == 0) return PG_OK;
+  if (!src) return fail(PG_ERR_ARG, "null text");
+  DeviceGuard g(c->device);
+  cudaPointerAttributes attr;
+  memset(&attr, 0, sizeof(attr));
+  cudaError_t pe = cudaPointerGetAttributes(&attr, src);
+  if (pe != cudaSuccess) {
+    cudaGetLastError();
+    attr.type = cudaMemoryTypeUnregistered;
+  }
+  const bool on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+  const bool pinned = attr.type == cudaMemoryTypeHost;
+  char first = 0;
+  if (on_device) PG_CUDA(cudaMemcpy(&first, src, 1, cudaMemcpyDeviceToHost));
+  else first = src[0];
+  int is_fastq;
+  if (first == '@') is_fastq = 1;
+  else if (first == '>') is_fastq = 0;
+  else return fail(PG_ERR_FORMAT, "unsupported sequence format: file must start with '>' (FASTA) or '@' (FASTQ)");
+
+  cudaEvent_t ev0, ev1;
+  PG_CUDA(cudaEventCreate(&ev0));
+  PG_CUDA(cudaEventCreate(&ev1));
+  // reset per-feed scalars: carry := 0 (FASTQ: header line phase; FASTA: LS_LINE_START)
+  PG_CUDA(cudaMemsetAsync(c->d_scalars + SC_CARRY, 0, sizeof(unsigned long long), c->stream));
+  PG_CUDA(cudaEventRecord(ev0, c->stream));
+  const bool direct = on_device && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (!direct) PG_TRY(ensure_stage(c, !on_device && !pinned));
+  int buf = 0;
+  for (uint64_t off = 0; off < len; off += CHUNK_BYTES, buf ^= 1) {
+    const uint64_t n = std::min<uint64_t>(CHUNK_BYTES, len - off);
+    const uint64_t nh = std::min<uint64_t>(CT_HALO, len - off - n);
+    const char* d_text;
+    if (direct) {
+      d_text = src + off;
+    } else {
+      // wait until the kernels of two chunks ago released this staging buffer
+      PG_CUDA(cudaEventSynchronize(c->stage_free[buf]));
+      if (on_device) {
+        PG_CUDA(cudaMemcpyAsync(c->d_stage[buf], src + off, n + nh, cudaMemcpyDeviceToDevice, c->copy_stream));
+      } else if (pinned) {
+        PG_CUDA(cudaMemcpyAsync(c->d_stage[buf], src + off, n + nh, cudaMemcpyHostToDevice, c->copy_stream));
+      } else {
+        memcpy(c->h_stage[buf], src + off, n + nh);
+        PG_CUDA(cudaMemcpyAsync(c->d_stage[buf], c->h_stage[buf], n + nh, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      PG_CUDA(cudaEventRecord(c->stage_ready[buf], c->copy_stream));
+      PG_CUDA(cudaStreamWaitEvent(c->stream, c->stage_ready[buf], 0));
+      d_text = c->d_stage[buf];
+    }
+    PG_TRY(launch_chunk(c, d_text, n, n + nh, is_fastq, op));
+    if (!direct) PG_CUDA(cudaEventRecord(c->stage_free[buf], c->stream));
+  }
+  PG_CUDA(cudaEventRecord(ev1, c->stream));
+  unsigned long long sc[SC_N];
+  PG_CUDA(cudaMemcpyAsync(sc, c->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+  PG_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  c->last_feed_ms = ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  c->kmers_seen = sc[SC_KMERS];
+  if (sc[SC_ERROR] & ERR_PROBE) return fail(PG_ERR_FULL, "k-mer table full: raise hash_size (-e)");
+  if (sc[SC_ERROR] & ERR_HALO) return fail(PG_ERR_FORMAT, "sequence layout not supported: more than 97 line breaks inside one k-mer");
+  if (sc[SC_DISTINCT] > c->max_distinct)
+    return fail(PG_ERR_FULL, "k-mer table over its design load: " + std::to_string(sc[SC_DISTINCT]) + " distinct k-mers > " + std::to_string(c->max_distinct) + "; raise hash_size (-e)");
+  return PG_OK;
+}
+
+static bool read_file(const char* path, std::vector<char>& out, std::string& err) {
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    err = std::string("File ") + path + " cannot be opened.";
+    return false;
+  }
+  fseek(f, 0, SEEK_END);
+  long long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize((size_t)sz);
+  size_t got = sz ? fread(out.data(), 1, (size_t)sz, f) : 0;
+  fclose(f);
+  if ((long long)got != sz) {
+    err = std::string("short read on ") + path;
+    return false;
+  }
+  return true;
+}
+
+static bool ends_with(const std::string& s, const std::string& e) { return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0; }
+
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" pg_counter* pg_count_new(uint32_t k, uint64_t max_distinct, int device) {
+  clear_error();
+  if (k < 1 || k > 32) {
+    fail(PG_ERR_ARG, "k must be in [1,32]");
+    return nullptr;
+  }
+  if (check_device(device) != PG_OK) return nullptr;
+  DeviceGuard g(device);
+  pg_counter* c = new pg_counter();
+  c->device = device;
+  c->k = k;
+  c->max_distinct = std::max<uint64_t>(max_distinct, 1024);
+  c->capacity = (uint64_t)((double)c->max_distinct / 0.6) + 1024;
+  c->capacity = (c->capacity + 3) & ~3ull;
+  auto bail = [&](const char* what, cudaError_t e) {
+    fail(PG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    pg_count_destroy(c);
+    return (pg_counter*)nullptr;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  }
+  if ((e = cudaMalloc((void**)&c->keys, c->capacity * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
+  if ((e = cudaMalloc((void**)&c->counts, c->capacity * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(counts)", e);
+  if ((e = cudaMalloc((void**)&c->d_scalars, SC_N * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(scalars)", e);
+  fill_keys_kernel<<<1184, 512, 0, c->stream>>>(c->keys, c->capacity);
+  count_launch();
+  cudaMemsetAsync(c->counts, 0, c->capacity * sizeof(uint32_t), c->stream);
+  cudaMemsetAsync(c->d_scalars, 0, SC_N * sizeof(unsigned long long), c->stream);
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail("table init", e);
+  return c;
+}
+
+extern "C" void pg_count_destroy(pg_counter* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->keys) cudaFree(c->keys);
+  if (c->counts) cudaFree(c->counts);
+  if (c->d_scalars) cudaFree(c->d_scalars);
+  if (c->d_tile_meta) cudaFree(c->d_tile_meta);
+  for (int i = 0; i < 2; ++i) {
+    if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+    if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
+    if (c->stage_ready[i]) cudaEventDestroy(c->stage_ready[i]);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" int pg_count_feed(pg_counter* c, const char* text, uint64_t len, int op) {
+  clear_error();
+  return feed_impl(c, text, len, op);
+}
+
+extern "C" int pg_count_feed_device(pg_counter* c, const char* d_text, uint64_t len, int op) {
+  clear_error();
+  return feed_impl(c, d_text, len, op);
+}
+
+extern "C" pg_counter* pg_count_create_from_buffers(const char* reads, uint64_t reads_len, const char* segments,
+                                                    uint64_t segments_len, uint32_t k, uint64_t hash_size, int device) {
+  clear_error();
+  if (!reads) {
+    fail(PG_ERR_ARG, "null reads buffer");
+    return nullptr;
+  }
+  // PRIME/UPDATE mode: every distinct key comes from the segment file, whose byte length bounds its
+  // number of k-mer windows; count-all mode: hash_size is the caller's bound (jellyfish would grow).
+  const uint64_t max_distinct = segments ? std::max<uint64_t>(segments_len, 1024)
+                                         : std::max<uint64_t>(hash_size, 1024);
+  pg_counter* c = pg_count_new(k, max_distinct, device);
+  if (!c) return nullptr;
+  int st;
+  if (segments) {
+    st = feed_impl(c, segments, segments_len, PG_OP_PRIME);
+    if (st == PG_OK) st = feed_impl(c, reads, reads_len, PG_OP_UPDATE);
+  } else {
+    st = feed_impl(c, reads, reads_len, PG_OP_COUNT);
+  }
+  if (st != PG_OK) {
+    pg_count_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" pg_counter* pg_count_create(const char* reads_path, const char* segments_path, uint32_t k,
+                                       uint64_t hash_size, int device) {
+  clear_error();
+  if (!reads_path) {
+    fail(PG_ERR_ARG, "null reads path");
+    return nullptr;
+  }
+  // check_input_file (src/commands.cpp:42-56): must exist and must not be gzip-compressed
+  for (const char* p : {reads_path, segments_path}) {
+    if (p && ends_with(p, ".gz")) {
+      fail(PG_ERR_IO, std::string("File ") + p + " seems to be gzip-compressed. PanGenie requires an uncompressed file.");
+      return nullptr;
+    }
+  }
+  std::vector<char> reads, segs;
+  std::string err;
+  if (!read_file(reads_path, reads, err) || (segments_path && !read_file(segments_path, segs, err))) {
+    fail(PG_ERR_IO, err);
+    return nullptr;
+  }
+  return pg_count_create_from_buffers(reads.data(), reads.size(), segments_path ? segs.data() : nullptr, segs.size(), k, hash_size, device);
+}
+
+static int lookup_codes(const pg_counter* c, const uint64_t* h_codes, uint64_t n, uint64_t* out) {
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  if (n == 0) return PG_OK;
+  DeviceGuard g(c->device);
+  uint64_t *d_codes = nullptr, *d_out = nullptr;
+  PG_CUDA(cudaMalloc((void**)&d_codes, n * 8));
+  cudaError_t e = cudaMalloc((void**)&d_out, n * 8);
+  if (e != cudaSuccess) {
+    cudaFree(d_codes);
+    return fail(PG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  // read-only on the table: a private stream keeps concurrent host threads independent
+  cudaStream_t s;
+  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  cudaMemcpyAsync(d_codes, h_codes, n * 8, cudaMemcpyHostToDevice, s);
+  const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+  lookup_kernel<<<grid, 256, 0, s>>>(d_codes, n, c->k, c->keys, c->counts, c->capacity, d_out);
+  count_launch();
+  cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  cudaStreamDestroy(s);
+  cudaFree(d_codes);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(PG_ERR_CUDA, std::string("lookup: ") + cudaGetErrorString(e));
+  return PG_OK;
+}
+
+extern "C" int pg_count_lookup(const pg_counter* c, const uint64_t* kmers, uint64_t n, uint64_t* out) {
+  clear_error();
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  const uint64_t mask = kmer_mask(c->k);
+  for (uint64_t i = 0; i < n; ++i)
+    if (kmers[i] & ~mask) return fail(PG_ERR_ARG, "k-mer code out of range for k");
+  return lookup_codes(c, kmers, n, out);
+}
+
+extern "C" int pg_count_lookup_ascii(const pg_counter* c, const char* kmers, uint64_t n, uint64_t* out) {
+  clear_error();
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  std::vector<uint64_t> codes(n);
+  std::vector<uint8_t> bad(n, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t v = 0;
+    bool ok = true;
+    for (uint32_t j = 0; j < c->k; ++j) {
+      char ch = kmers[i * c->k + j];
+      uint64_t code;
+      switch (ch) {
+        case 'A': case 'a': code = 0; break;
+        case 'C': case 'c': code = 1; break;
+        case 'G': case 'g': code = 2; break;
+        case 'T': case 't': code = 3; break;
+        default: code = 0; ok = false;
+      }
+      v = (v << 2) | code;
+    }
+    codes[i] = ok ? v : 0;
+    bad[i] = !ok;
+  }
+  PG_TRY(lookup_codes(c, codes.data(), n, out));
+  for (uint64_t i = 0; i < n; ++i)
+    if (bad[i]) out[i] = 0;  // not a DNA k-mer: absent
+  return PG_OK;
+}
+
+extern "C" int pg_count_histogram(const pg_counter* c, uint64_t max_count, uint64_t* bins) {
+  clear_error();
+  if (!c || !bins) return fail(PG_ERR_ARG, "null argument");
+  DeviceGuard g(c->device);
+  unsigned long long* d_bins = nullptr;
+  PG_CUDA(cudaMalloc((void**)&d_bins, (max_count + 1) * 8));
+  cudaMemsetAsync(d_bins, 0, (max_count + 1) * 8, c->stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, c->stream);
+  histogram_kernel<<<148 * 2, 512, 0, c->stream>>>(c->counts, c->capacity, max_count, d_bins);
+  count_launch();
+  cudaEventRecord(e1, c->stream);
+  cudaMemcpyAsync(bins, d_bins, (max_count + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_bins);
+  if (e != cudaSuccess) return fail(PG_ERR_CUDA, std::string("histogram: ") + cudaGetErrorString(e));
+  bins[0] = 0;
+  return PG_OK;
+}
+
+extern "C" int pg_count_kmer_coverage(const pg_counter* c, uint64_t genome_kmers, uint64_t* out) {
+  clear_error();
+  if (!c || !out || genome_kmers == 0) return fail(PG_ERR_ARG, "invalid argument");
+  DeviceGuard g(c->device);
+  cudaMemsetAsync(c->d_scalars + SC_COUNT_SUM, 0, 8, c->stream);
+  count_sum_kernel<<<148 * 2, 512, 0, c->stream>>>(c->counts, c->capacity, c->d_scalars);
+  count_launch();
+  unsigned long long s = 0;
+  cudaMemcpyAsync(&s, c->d_scalars + SC_COUNT_SUM, 8, cudaMemcpyDeviceToHost, c->stream);
+  PG_CUDA(cudaStreamSynchronize(c->stream));
+  // the reference accumulates count/genome in long double and takes the ceiling (jellyfishcounter.cpp:106-117)
+  long double r = (long double)s / (long double)genome_kmers;
+  uint64_t fl = (uint64_t)r;
+  *out = ((long double)fl < r) ? fl + 1 : fl;
+  return PG_OK;
+}
+
+extern "C" int pg_count_compute_histogram(const pg_counter* c, uint64_t max_count, int largest_peak,
+                                          const char* filename, uint64_t* peak) {
+  clear_error();
+  if (!peak) return fail(PG_ERR_ARG, "null peak");
+  std::vector<uint64_t> bins(max_count + 1);
+  PG_TRY(pg_count_histogram(c, max_count, bins.data()));
+  if (filename && *filename) {  // Histogram::write_to_file (src/histogram.cpp:32-39)
+    std::ofstream f(filename);
+    if (!f.good()) return fail(PG_ERR_IO, std::string("JellyfishCounter::computeHistogram: File ") + filename + " cannot be created.");
+    for (uint64_t i = 0; i <= max_count; ++i) f << i << '\t' << bins[i] << '\n';
+  }
+  PG_TRY(pg_histogram_peak(bins.data(), bins.size(), largest_peak, peak));
+  if (filename && *filename) {  // src/jellyfishcounter.cpp:142-150
+    std::ofstream f(filename, std::ios::app);
+    f << "parameters\t" << *peak / 2.0 << '\t' << *peak << std::endl;
+  }
+  return PG_OK;
+}
+
+extern "C" uint64_t pg_count_distinct(const pg_counter* c) {
+  if (!c) return 0;
+  DeviceGuard g(c->device);
+  unsigned long long d = 0;
+  cudaMemcpy(&d, c->d_scalars + SC_DISTINCT, 8, cudaMemcpyDeviceToHost);
+  return d;
+}
+
+extern "C" uint64_t pg_count_capacity(const pg_counter* c) { return c ? c->capacity : 0; }
+
+extern "C" int pg_count_device_arrays(const pg_counter* c, uint64_t* keys_addr, uint64_t* counts_addr, uint64_t* capacity) {
+  clear_error();
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  if (keys_addr) *keys_addr = (uint64_t)(uintptr_t)c->keys;
+  if (counts_addr) *counts_addr = (uint64_t)(uintptr_t)c->counts;
+  if (capacity) *capacity = c->capacity;
+  return PG_OK;
+}
+
+extern "C" uint64_t pg_count_kmers_seen(const pg_counter* c) { return c ? c->kmers_seen : 0; }
+extern "C" double pg_count_last_ms(const pg_counter* c) { return c ? c->last_feed_ms : 0.0; }

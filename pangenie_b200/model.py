@@ -1,0 +1,280 @@
+"""Host-side mirror of the reference's interface for the genotyping hot path, over the C-ABI.
+
+Names and argument meaning follow the reference (file:line into the reference tree):
+  KmerCounter / JellyfishCounter   src/kmercounter.hpp:9-24, src/jellyfishcounter.cpp:26-153
+  ProbabilityTable                 src/probabilitytable.hpp:12-30
+  HMM                              src/hmm.hpp:26-47
+Everything computes on the GPU through libpangenie_b200.so; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import PG_OK, PgGenotypeInput, PgHmmParams, PgHmmResult, PgPanel, PgProbTable, PgTimings, ptr
+from .panel import Panel, Result
+
+
+class PgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pangenie_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(lib, st: int):
+    if st != PG_OK:
+        raise PgError(st, lib.pg_last_error().decode())
+
+
+def _bytes_arg(b):
+    """(address, length, keepalive) for bytes / bytearray / numpy uint8 / torch uint8 tensors."""
+    if b is None:
+        return None, 0, None
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b.view(np.uint8))
+        return a.ctypes.data, a.size, a
+    if hasattr(b, "data_ptr"):  # torch tensor (host pinned or device)
+        return b.data_ptr(), b.numel() * b.element_size(), b
+    a = np.frombuffer(b, dtype=np.uint8)
+    return a.ctypes.data, a.size, a
+
+
+class ProbabilityTable:
+    """ProbabilityTable(cov_min, cov_max, count_max, regularization_const) (src/probabilitytable.cpp:28-45)."""
+
+    def __init__(self, cov_min: int, cov_max: int, count_max: int, regularization_const: float):
+        self._lib = capi.load()
+        self.t = PgProbTable()
+        _check(self._lib, self._lib.pg_probtable_init(C.byref(self.t), cov_min, cov_max, count_max, regularization_const))
+
+    def modify_probability(self, kmer_coverage: int, read_kmer_count: int, p0: float, p1: float, p2: float):
+        """modify_probability(cov, count, CopyNumber(p0,p1,p2)) (src/probabilitytable.cpp:67-73)."""
+        _check(self._lib, self._lib.pg_probtable_modify(C.byref(self.t), kmer_coverage, read_kmer_count, p0, p1, p2))
+
+    def get_probability(self, kmer_coverage: int, read_kmer_count: int):
+        return tuple(self._lib.pg_probtable_get(C.byref(self.t), kmer_coverage, read_kmer_count, cn) for cn in range(3))
+
+    def __del__(self):
+        try:
+            self._lib.pg_probtable_free(C.byref(self.t))
+        except Exception:
+            pass
+
+
+def copy_number(p0, p1, p2, regularization=None):
+    """CopyNumber(cn_0, cn_1, cn_2[, regularization_const]) (src/copynumber.cpp:14-28) -> (p0, p1, p2)."""
+    if regularization is None:
+        return (p0, p1, p2)
+    s = p0 + p1 + p2 + 3.0 * regularization
+    a, b = (p0 + regularization) / s, (p1 + regularization) / s
+    return (a, b, 1.0 - a - b)
+
+
+class KmerCounter:
+    """JellyfishCounter (src/jellyfishcounter.cpp:26-153) on the device k-mer table."""
+
+    def __init__(self, reads=None, segments=None, kmer_size: int = 31, hash_size: int = 3_000_000_000, device: int = 0,
+                 max_distinct: int | None = None):
+        self._lib = capi.load()
+        self.k = kmer_size
+        self._h = None
+        if reads is None:
+            h = self._lib.pg_count_new(kmer_size, max_distinct or hash_size, device)
+        elif isinstance(reads, str):
+            h = self._lib.pg_count_create(reads.encode(), segments.encode() if segments else None, kmer_size, hash_size, device)
+        else:
+            ra, rl, _k1 = _bytes_arg(reads)
+            sa, sl, _k2 = _bytes_arg(segments)
+            h = self._lib.pg_count_create_from_buffers(ra, rl, sa, sl, kmer_size, hash_size, device)
+        if not h:
+            raise PgError(-1, self._lib.pg_last_error().decode())
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def feed(self, text, op: int):
+        a, n, _keep = _bytes_arg(text)
+        on_device = hasattr(text, "is_cuda") and text.is_cuda
+        f = self._lib.pg_count_feed_device if on_device else self._lib.pg_count_feed
+        _check(self._lib, f(self._h, a, n, op))
+
+    def getKmerAbundance(self, kmer: str) -> int:
+        out = np.zeros(1, np.uint64)
+        b = np.frombuffer(kmer.encode(), dtype=np.uint8)
+        assert len(b) == self.k
+        _check(self._lib, self._lib.pg_count_lookup_ascii(self._h, b.ctypes.data, 1, out.ctypes.data))
+        return int(out[0])
+
+    def lookup(self, codes: np.ndarray) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        out = np.zeros(len(codes), np.uint64)
+        _check(self._lib, self._lib.pg_count_lookup(self._h, ptr(codes), len(codes), ptr(out)))
+        return out
+
+    def computeKmerCoverage(self, genome_kmers: int) -> int:
+        out = C.c_uint64(0)
+        _check(self._lib, self._lib.pg_count_kmer_coverage(self._h, genome_kmers, C.byref(out)))
+        return out.value
+
+    def histogram(self, max_count: int = 10000) -> np.ndarray:
+        bins = np.zeros(max_count + 1, np.uint64)
+        _check(self._lib, self._lib.pg_count_histogram(self._h, max_count, ptr(bins)))
+        return bins
+
+    def computeHistogram(self, max_count: int, largest_peak: bool, filename: str = "") -> int:
+        out = C.c_uint64(0)
+        _check(self._lib, self._lib.pg_count_compute_histogram(self._h, max_count, int(largest_peak),
+                                                                 filename.encode() if filename else None, C.byref(out)))
+        return out.value
+
+    def distinct(self) -> int:
+        return int(self._lib.pg_count_distinct(self._h))
+
+    def capacity(self) -> int:
+        return int(self._lib.pg_count_capacity(self._h))
+
+    def kmers_seen(self) -> int:
+        return int(self._lib.pg_count_kmers_seen(self._h))
+
+    def last_ms(self) -> float:
+        return float(self._lib.pg_count_last_ms(self._h))
+
+    def device_arrays(self):
+        k, c, cap = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib, self._lib.pg_count_device_arrays(self._h, C.byref(k), C.byref(c), C.byref(cap)))
+        return k.value, c.value, cap.value
+
+    def close(self):
+        if self._h:
+            self._lib.pg_count_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hmm_params(recombrate=1.26, uniform=False, effective_N=25000.0, only_paths=None, normalize=True):
+    """Arguments of HMM::HMM (src/hmm.hpp:38) after `probabilities`/`run_*`; returns (struct, keepalive)."""
+    p = PgHmmParams()
+    p.recombrate = float(recombrate)
+    p.effective_N = float(effective_N)
+    p.uniform = int(bool(uniform))
+    p.normalize = int(bool(normalize))
+    keep = None
+    if only_paths is not None:
+        keep = np.ascontiguousarray(only_paths, dtype=np.uint16)
+        p.only_paths = keep.ctypes.data
+        p.n_only_paths = len(keep)
+    return p, keep
+
+
+class Engine:
+    """Per-device engine (pg_engine)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = capi.load()
+        self._h = self._lib.pg_engine_create(device)
+        if not self._h:
+            raise PgError(-1, self._lib.pg_last_error().decode())
+        self.device = device
+
+    def _panel_array(self, panels):
+        arr = (PgPanel * len(panels))()
+        for i, p in enumerate(panels):
+            arr[i] = p.as_struct()
+        return arr
+
+    def hmm_run(self, panels, table: ProbabilityTable, results=None, **kw):
+        """HMM forward-backward for a list of chromosome panels -> list[Result]."""
+        if results is None:
+            results = [Result(p) for p in panels]
+        prm, _keep = hmm_params(**kw)
+        pa = self._panel_array(panels)
+        ra = (PgHmmResult * len(panels))()
+        for i, r in enumerate(results):
+            ra[i] = r.as_struct()
+        _check(self._lib, self._lib.pg_hmm_run(self._h, len(panels), pa, C.byref(table.t), C.byref(prm), ra))
+        return results
+
+    def emission_run(self, panel: Panel, table: ProbabilityTable):
+        """EmissionProbabilityComputer for every variant -> (offsets, dense (maxA+1)^2 matrices, log_scale)."""
+        V = panel.n_variants
+        off = np.zeros(V + 1, np.uint64)
+        for v in range(V):
+            n = panel.nr_alleles(v)
+            off[v + 1] = off[v] + n * n
+        em = np.zeros(int(off[-1]), np.float64)
+        ls = np.zeros(V, np.float64)
+        ps = panel.as_struct()
+        _check(self._lib, self._lib.pg_emission_run(self._h, C.byref(ps), C.byref(table.t), ptr(off), ptr(em), ptr(ls)))
+        return off, em, ls
+
+    def fill_counts(self, counter: KmerCounter, kmer_abundance_peak: int, panels):
+        pa = self._panel_array(panels)
+        _check(self._lib, self._lib.pg_fill_counts(self._h, counter.handle, kmer_abundance_peak, len(panels), pa))
+
+    def genotype_run(self, reads, segments, panels, k=31, hash_size=3_000_000_000, regularization=0.01,
+                     histogram_path=None, results=None, **kw):
+        """The `PanGenie -f` stage (src/commands.cpp:730-1084) with host buffers -> (results, peak)."""
+        if results is None:
+            results = [Result(p) for p in panels]
+        prm, _keep = hmm_params(**kw)
+        inp = PgGenotypeInput()
+        ra_, rl, _k1 = _bytes_arg(reads)
+        sa, sl, _k2 = _bytes_arg(segments)
+        inp.reads, inp.reads_len, inp.segments, inp.segments_len = ra_, rl, sa, sl
+        inp.k, inp.hash_size, inp.regularization = k, hash_size, regularization
+        inp.histogram_path = histogram_path.encode() if histogram_path else None
+        pa = self._panel_array(panels)
+        ra = (PgHmmResult * len(panels))()
+        for i, r in enumerate(results):
+            ra[i] = r.as_struct()
+        peak = C.c_uint64(0)
+        _check(self._lib, self._lib.pg_genotype_run(self._h, C.byref(inp), len(panels), pa, C.byref(prm), ra, C.byref(peak)))
+        return results, peak.value
+
+    def timings(self) -> dict:
+        t = PgTimings()
+        _check(self._lib, self._lib.pg_engine_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in PgTimings._fields_}
+
+    def close(self):
+        if self._h:
+            self._lib.pg_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HMM:
+    """HMM(unique_kmers, probabilities, run_genotyping, run_phasing, recombrate, uniform, effective_N,
+    only_paths, normalize) (src/hmm.hpp:38).  Viterbi phasing is out of scope."""
+
+    _engines: dict = {}
+
+    def __init__(self, unique_kmers: Panel, probabilities: ProbabilityTable, run_genotyping=True, run_phasing=False,
+                 recombrate=1.26, uniform=False, effective_N=25000.0, only_paths=None, normalize=True, device=0):
+        if run_phasing:
+            raise NotImplementedError("Viterbi phasing (-p) is outside the accelerated path")
+        eng = HMM._engines.get(device)
+        if eng is None:
+            eng = HMM._engines[device] = Engine(device)
+        self.panel = unique_kmers
+        self.result = Result(unique_kmers)
+        if run_genotyping:
+            eng.hmm_run([unique_kmers], probabilities, [self.result], recombrate=recombrate, uniform=uniform,
+                        effective_N=effective_N, only_paths=only_paths, normalize=normalize)
+
+    def get_genotyping_result(self) -> Result:
+        return self.result
