@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — variants genotyped per second through the `PanGenie -f` hot path on B200.
+
+One "step" = one pass of the whole stage (PRIME segments, count reads, histogram peak, fill, emission,
+forward-backward, finalize) over one synthetic sample of the named workload.
+
+  value   whole-job variants/s with every input already resident in HBM (pg_engine_run_resident)
+  e2e     the same through the reference-facing C-ABI call pg_genotype_run with PINNED HOST buffers:
+          host->device copies of reads / segments / panel and device->host copies of the results are
+          inside the timed region
+  roofline  dominant kernel (by measured device time): algorithmic bytes / CUDA-event duration vs the
+          measured HBM peak of MEASURED_PEAKS.json
+  cpu_baseline  the reference's own hmm.cpp (oracle/_ref) for emission+HMM and the CPU restatement of the
+          jellyfish path for counting, timed on this box's host cores on a bounded sample
+
+Multi-GPU (`torchrun ... bench.py --gpus N`): workloads with one chromosome cannot shard, so every rank
+genotypes its own sample of the same shape (weak scaling: the production scenario of one index, many
+samples, reference README.md:128); 22-chromosome workloads shard chromosomes LPT-wise and reads by record
+ranges, with one NCCL broadcast (primed keys) and one all-reduce (counts) — see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_chrom, n_variants, n_haplotypes, coverage)  — BASELINE.json configs[1..]
+    "cfg2": (1, 10_000, 8, 10.0),
+    "cfg2x8": (1, 80_000, 8, 10.0),
+    "cfg3s": (22, 100_000, 32, 30.0),   # configs[2] at 1/10 of the variants (same per-column shape)
+    "h64s": (22, 50_000, 64, 30.0),     # configs[3] shape at 1/100 of the variants
+}
+WORKLOAD_TEXT = {
+    "cfg2": "synthetic 1 chrom, 10k variants, 8 haplotypes, 10x reads, k=31 (BASELINE.json configs[1])",
+    "cfg2x8": "synthetic 1 chrom, 80k variants, 8 haplotypes, 10x reads, k=31",
+    "cfg3s": "synthetic 22 chroms, 100k variants, 32 haplotypes, 30x reads, k=31 (configs[2] shape, 1/10 variants)",
+    "h64s": "synthetic 22 chroms, 50k variants, 64 haplotypes, 30x reads, k=31 (configs[3] shape, 1/100 variants)",
+}
+
+
+def fb_bytes_per_column(P: int, A: int = 2) -> float:
+    """B_fb = 2*8*P^2 + 2*2*P + 2*8*A^2 + 8 + 8*A(A+1)/2."""
+    return 2 * 8 * P * P + 2 * 2 * P + 2 * 8 * A * A + 8 + 8 * A * (A + 1) / 2
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_workload(name: str, seed_offset: int = 0):
+    from pangenie_b200 import synth
+    n_chrom, n_var, n_hap, cov = WORKLOADS[name]
+    return synth.make_workload(n_chrom=n_chrom, n_variants=n_var, n_haplotypes=n_hap, coverage=cov, seed=20260925 + 1 + seed_offset)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own code (oracle/_ref) for emission + HMM, restated jellyfish path for counting
+# ------------------------------------------------------------------------------------------------------
+def cpu_pipeline(wl, threads: int, sample_bytes: int, filled_panels_ok: bool):
+    from tests import oracles
+    import pangenie_b200 as pg
+    oracle = oracles.load_oracle()
+    ref = oracles.load_ref()
+    rec = wl.record_bytes
+    total = len(wl.reads_fastq)
+    sample = min(total, max(rec, (sample_bytes // rec) * rec))
+    t0 = time.perf_counter()
+    oc = oracles.OracleCounter(oracle, None, None, wl.k)
+    oc.feed(wl.segments_fasta, pg.PG_OP_PRIME, threads=threads)
+    t_prime = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oc.feed(wl.reads_fastq[:sample], pg.PG_OP_UPDATE, threads=threads)
+    t_update_sample = time.perf_counter() - t0
+    t_update = t_update_sample * total / sample
+    # the HMM needs counts of the FULL read set: taken from the panels as filled by the GPU run (bit-identical
+    # to the oracle's, tests/test_gpu_pipeline.py) so the CPU arm genotypes the same filled panel
+    t0 = time.perf_counter()
+    if not filled_panels_ok:
+        peak = oc.computeHistogram(10000, True)
+        oc.fill_counts(peak, wl.panels)
+    t_fill = time.perf_counter() - t0
+    peak = max(int(np.median(np.concatenate([p.coverage for p in wl.panels]))), 4)
+    table = pg.ProbabilityTable(peak // 4, peak * 4, 2 * peak, 0.01)
+    hthreads = min(threads, len(wl.panels))
+    t0 = time.perf_counter()
+    if ref is not None:
+        oracles.cpu_hmm_run(ref, "pgr_", wl.panels, table, threads=hthreads, recombrate=1.26, effective_N=1e-5)
+        kind = "reference"
+    else:
+        oracles.cpu_hmm_run(oracle, "pgo_", wl.panels, table, threads=hthreads, recombrate=1.26, effective_N=1e-5)
+        kind = "port"
+    t_hmm = time.perf_counter() - t0
+    t_total = t_prime + t_update + t_fill + t_hmm
+    return {
+        "value": wl.n_variants / t_total, "unit": "variants/s", "cores": threads, "kind": kind,
+        "sample": (f"emission+HMM: reference hmm.cpp on the full panel, {hthreads} thread(s) (one per chromosome, commands.cpp:949-978), "
+                   f"{t_hmm:.3f}s; counting: CPU restatement of the jellyfish path (not libjellyfish), {threads} threads, PRIME full segments "
+                   f"{t_prime:.2f}s + UPDATE on the first {sample / 1e6:.1f} MB of {total / 1e6:.1f} MB reads {t_update_sample:.2f}s "
+                   f"extrapolated linearly to {t_update:.2f}s; fill {t_fill:.3f}s"),
+        "seconds": {"prime": t_prime, "update_extrapolated": t_update, "fill": t_fill, "hmm": t_hmm},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PG_BENCH_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-mb", type=float, default=24.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    K = args.steps
+    n_chrom, n_var, n_hap, cov = WORKLOADS[args.workload]
+    config = {"workload": WORKLOAD_TEXT[args.workload], "k": 31, "paths": n_hap + 1, "recombrate": 1.26, "effective_N": 1e-5,
+              "regularization": 0.01, "count_only_graph": True,
+              "multi_gpu": "one sample per GPU (weak scaling over samples), no collective on the data path"}
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = load_workload(args.workload)
+        threads = os.cpu_count() or 1
+        vals = []
+        t_all0 = time.perf_counter()
+        last = None
+        for i in range(W + K):
+            last = cpu_pipeline(wl, threads, int(args.cpu_sample_mb * 1e6), filled_panels_ok=False)
+            if i >= W:
+                vals.append(last["value"])
+        v = float(np.mean(vals)) if vals else float("nan")
+        line = {"metric": "variants genotyped per second (end-to-end PanGenie -f stage)", "value": v, "unit": "variants/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * wl.n_variants / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f80 (x87 long double)", "data": "synthetic", "config": config,
+                "impl": "reference", "cpu_baseline": {**last, "value": v},
+                "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.perf_counter() - t_all0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import pangenie_b200 as pg
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = load_workload(args.workload, seed_offset=rank)  # every rank its own sample of the same shape
+    V = wl.n_variants
+    eng = pg.Engine(local)
+    kw = dict(recombrate=1.26, effective_N=1e-5)
+    reads_h = torch.from_numpy(wl.reads_fastq).pin_memory()
+    segs_h = torch.from_numpy(wl.segments_fasta).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    reads_d = reads_h.cuda()
+    segs_d = segs_h.cuda()
+    results = eng.load(wl.panels)
+    for _ in range(W):
+        eng.run_resident(reads_d, segs_d, k=wl.k, **kw)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    tm_acc = {}
+    t0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()  # evict L2 between steps (256 MiB > 126 MB L2)
+        eng.run_resident(reads_d, segs_d, k=wl.k, **kw)
+        t = eng.timings()
+        for k_, v_ in t.items():
+            tm_acc[k_] = tm_acc.get(k_, 0) + v_
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    eng.fetch()
+    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item())
+    value = world * V * K / dt
+
+    # ---- e2e: pinned host buffers through pg_genotype_run, copies inside the timed region ----
+    for _ in range(2):
+        eng.genotype_run(reads_h, segs_h, wl.panels, k=wl.k, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()
+        res_e2e, peak = eng.genotype_run(reads_h, segs_h, wl.panels, k=wl.k, **kw)
+    barrier()
+    dte = time.perf_counter() - t0
+    tmax = torch.tensor([dte], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dte = float(tmax.item())
+    e2e_value = world * V * K / dte
+    panel_bytes = sum(sum(getattr(p, n).nbytes for n in ("positions", "path_to_allele", "kmer_offsets", "allele_offsets", "allele_ids",
+                                                           "allele_undefined", "allele_kmer_offset", "allele_kmer_mask", "kmer_codes",
+                                                           "flank_offsets", "flank_codes")) for p in wl.panels)
+    h2d = int(reads_h.numel() + segs_h.numel() + panel_bytes)
+    d2h = int(sum(r.likelihoods.nbytes + r.is_column.nbytes + r.genotype.nbytes + r.quality.nbytes + r.unique_kmers.nbytes + r.coverage.nbytes
+                  for r in res_e2e) + sum(p.kmer_counts.nbytes + p.coverage.nbytes for p in wl.panels))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per launch = per step, CUDA events on the launching stream) ----
+    peak_gbs, peak_src = measured_peak_gbs()
+    per = {k_: v_ / K for k_, v_ in tm_acc.items()}
+    P = n_hap + 1
+    kernels = {
+        "count_tile_kernel<UPDATE>": {"ms": per["count_ms"], "alg_bytes": per["text_bytes"] + 16.0 * per["kmers_counted"]},
+        "block_kernel (forward-backward)": {"ms": per["hmm_blocks_ms"], "alg_bytes": fb_bytes_per_column(P) * per["hmm_columns"]},
+        "skeleton_kernel": {"ms": per["hmm_skeleton_ms"], "alg_bytes": 0.0},
+        "count_tile_kernel<PRIME>": {"ms": per["prime_ms"], "alg_bytes": float(len(wl.segments_fasta)) * 17.0},
+        "fill": {"ms": per["fill_ms"], "alg_bytes": 0.0}, "emission+descriptors": {"ms": per["emission_ms"], "alg_bytes": 0.0},
+    }
+    for kk in kernels.values():
+        kk["gbs"] = kk["alg_bytes"] / (kk["ms"] * 1e-3) / 1e9 if kk["ms"] > 0 else 0.0
+    dom = max(("count_tile_kernel<UPDATE>", "block_kernel (forward-backward)"), key=lambda n: kernels[n]["ms"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
+                "frac": kernels[dom]["gbs"] / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
+                "forward_backward": {"achieved": kernels["block_kernel (forward-backward)"]["gbs"],
+                                     "frac": kernels["block_kernel (forward-backward)"]["gbs"] / peak_gbs,
+                                     "bytes_per_column": fb_bytes_per_column(P), "columns": per["hmm_columns"],
+                                     "ms": per["hmm_blocks_ms"], "skeleton_ms": per["hmm_skeleton_ms"]},
+                "stage_ms": {k_: per[k_] for k_ in ("prime_ms", "count_ms", "histogram_ms", "fill_ms", "emission_ms", "hmm_skeleton_ms",
+                                                     "hmm_blocks_ms", "finalize_ms")}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_pipeline(wl, os.cpu_count() or 1, int(args.cpu_sample_mb * 1e6), filled_panels_ok=True)
+
+    line = {"metric": "variants genotyped per second (end-to-end PanGenie -f stage)", "value": value, "unit": "variants/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {**config, "l2_flush": "256 MiB memset between steps"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dte / K},
+            "gpu_launches": int(tm_acc["kernel_launches"]), "roofline": roofline, "cpu_baseline": cpu,
+            "kmer_abundance_peak": int(peak)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -251,12 +251,28 @@ typedef struct {
 int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32_t n_chrom, pg_panel* panels,
                     const pg_hmm_params* params, pg_hmm_result* results, uint64_t* kmer_abundance_peak);
 
+/* ---- resident form: inputs already in HBM (what bench.py times as `value`) ----------------------------
+ * pg_engine_load uploads the panels (with k-mer codes) once; pg_engine_run_resident executes the whole
+ * `PanGenie -f` stage from DEVICE-resident read / segment text without any host<->device bulk copy;
+ * pg_engine_fetch downloads counts, coverage and results into the caller's buffers. */
+int pg_engine_load(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_hmm_result* layouts);
+int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_t reads_len, const char* d_segments,
+                           uint64_t segments_len, uint32_t k, uint64_t hash_size, double regularization,
+                           const pg_hmm_params* params, uint64_t* kmer_abundance_peak);
+int pg_engine_fetch(pg_engine* e, uint32_t n_chrom, pg_panel* panels, pg_hmm_result* results);
+
+/** Empties a counter (all keys removed, counts zero) so its HBM allocation can be reused. */
+int pg_count_clear(pg_counter* c);
+
 /* ---- measurement hooks (bench.py): per-stage device times of the last call on this engine ---- */
 typedef struct {
   double count_ms, histogram_ms, fill_ms, emission_ms, hmm_skeleton_ms, hmm_blocks_ms, finalize_ms;
   uint64_t hmm_columns;        /* HMM columns processed                                            */
   uint64_t hmm_block_launches; /* kernel launches of the block forward-backward kernel             */
   uint64_t kernel_launches;    /* all kernels launched by the last call                            */
+  uint64_t kmers_counted;      /* k-mers streamed through the UPDATE/COUNT pass                     */
+  uint64_t text_bytes;         /* read text bytes streamed                                          */
+  double prime_ms;             /* PRIME pass over the segment file                                  */
 } pg_timings;
 int pg_engine_timings(const pg_engine* e, pg_timings* out);
 

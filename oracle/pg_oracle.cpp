@@ -6,6 +6,8 @@
 #include "pg_oracle.h"
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -39,10 +41,87 @@ extern "C" const char* pgo_last_error(void) { return g_err.c_str(); }
  *     'N' so k-mers never span records; FASTQ quality is skipped by LENGTH (so '@'/'+' inside the
  *     quality string are harmless) and multi-line FASTQ is accepted.
  * ================================================================================================= */
+/* Lock-free open-addressing table (linear probing, power-of-two capacity) so the CPU baseline counts at a
+ * rate comparable to jellyfish's own lock-free hash; resized (single-threaded) before a feed when the text
+ * could overflow it. */
 struct pgo_counter {
-  uint32_t k;
-  std::unordered_map<uint64_t, uint64_t> table;
-  std::mutex mu;
+  uint32_t k = 0;
+  uint64_t cap = 0, mask = 0;
+  std::unique_ptr<std::atomic<uint64_t>[]> keys;
+  std::unique_ptr<std::atomic<uint64_t>[]> vals;
+  std::atomic<uint64_t> distinct{0};
+  static constexpr uint64_t EMPTY = ~0ULL;
+
+  static uint64_t mix(uint64_t h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+    return h;
+  }
+  void alloc(uint64_t c) {
+    cap = 1024;
+    while (cap < c) cap <<= 1;
+    mask = cap - 1;
+    keys.reset(new std::atomic<uint64_t>[cap]);
+    vals.reset(new std::atomic<uint64_t>[cap]);
+    for (uint64_t i = 0; i < cap; ++i) {
+      keys[i].store(EMPTY, std::memory_order_relaxed);
+      vals[i].store(0, std::memory_order_relaxed);
+    }
+  }
+  void reserve(uint64_t want_distinct) {
+    const uint64_t need = (uint64_t)(want_distinct / 0.5) + 1024;
+    if (need <= cap) return;
+    pgo_counter old;
+    old.cap = cap; old.keys.swap(keys); old.vals.swap(vals);
+    alloc(need);
+    for (uint64_t i = 0; i < old.cap; ++i) {
+      const uint64_t key = old.keys[i].load(std::memory_order_relaxed);
+      if (key == EMPTY) continue;
+      uint64_t s = mix(key) & mask;
+      while (keys[s].load(std::memory_order_relaxed) != EMPTY) s = (s + 1) & mask;
+      keys[s].store(key, std::memory_order_relaxed);
+      vals[s].store(old.vals[i].load(std::memory_order_relaxed), std::memory_order_relaxed);
+    }
+  }
+  // returns the slot of `key`, inserting it if `insert`; -1 if absent
+  int64_t find(uint64_t key, bool insert) {
+    uint64_t s = mix(key) & mask;
+    while (true) {
+      uint64_t cur = keys[s].load(std::memory_order_acquire);
+      if (cur == key) return (int64_t)s;
+      if (cur == EMPTY) {
+        if (!insert) return -1;
+        if (keys[s].compare_exchange_strong(cur, key, std::memory_order_acq_rel)) {
+          distinct.fetch_add(1, std::memory_order_relaxed);
+          return (int64_t)s;
+        }
+        if (cur == key) return (int64_t)s;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+  int64_t find_const(uint64_t key) const {
+    if (!cap) return -1;
+    uint64_t s = mix(key) & mask;
+    while (true) {
+      const uint64_t cur = keys[s].load(std::memory_order_relaxed);
+      if (cur == key) return (int64_t)s;
+      if (cur == EMPTY) return -1;
+      s = (s + 1) & mask;
+    }
+  }
+  void apply(uint64_t key, int op) {
+    if (op == PG_OP_UPDATE) {
+      const int64_t s = find(key, false);
+      if (s >= 0) vals[s].fetch_add(1, std::memory_order_relaxed);
+    } else {
+      const int64_t s = find(key, true);
+      if (op == PG_OP_COUNT) vals[s].fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+  uint64_t get(uint64_t key) const {
+    const int64_t s = find_const(key);
+    return s < 0 ? 0 : vals[s].load(std::memory_order_relaxed);
+  }
 };
 
 namespace {
@@ -159,18 +238,6 @@ bool encode_ascii(const char* s, uint32_t k, uint64_t* out) {
   return true;
 }
 
-template <class Map>
-void apply_op(Map& table, uint64_t key, int op) {
-  if (op == PG_OP_COUNT) {
-    ++table[key];
-  } else if (op == PG_OP_PRIME) {
-    table.emplace(key, 0);
-  } else {
-    auto it = table.find(key);
-    if (it != table.end()) ++it->second;
-  }
-}
-
 }  // namespace
 
 extern "C" pgo_counter* pgo_count_new(uint32_t k) {
@@ -180,31 +247,21 @@ extern "C" pgo_counter* pgo_count_new(uint32_t k) {
   }
   pgo_counter* c = new pgo_counter();
   c->k = k;
+  c->alloc(1024);
   return c;
 }
 
-extern "C" int pgo_count_feed(pgo_counter* c, const char* text, uint64_t len, int op) {
-  if (!c) return fail(PG_ERR_ARG, "null counter");
-  auto sink = [&](uint64_t key) { apply_op(c->table, key, op); };
-  KmerRoller<decltype(sink)> roller(c->k, sink);
-  return parse_records(text, len, [&](char ch) { roller(ch); });
-}
-
-/* Multi-threaded variant for the CPU baseline: the buffer is cut at record starts, every thread counts
- * into a private map restricted to... (UPDATE: read-only probe of the shared primed key set + private
- * increments; COUNT/PRIME: private maps) and the partial maps are merged. */
-extern "C" int pgo_count_feed_mt(pgo_counter* c, const char* text, uint64_t len, int op, int threads) {
-  if (!c) return fail(PG_ERR_ARG, "null counter");
-  if (threads <= 1 || len < (1u << 20)) return pgo_count_feed(c, text, len, op);
-  const bool fastq = text[0] == '@';
-  // record-aligned cut points
+namespace {
+/* record-aligned cut points for multi-threaded parsing */
+std::vector<uint64_t> record_cuts(const char* text, uint64_t len, int threads) {
   std::vector<uint64_t> cuts{0};
+  if (len == 0) return {0, 0};
+  const bool fastq = text[0] == '@';
   for (int t = 1; t < threads; ++t) {
     uint64_t p = len / threads * t;
-    // advance to a line start
-    while (p < len && text[p - 1] != '\n') ++p;
+    while (p < len && p > 0 && text[p - 1] != '\n') ++p;
     if (fastq) {
-      // a record starts at a line beginning with '@' whose line+2 begins with '+'
+      // a record starts at a line beginning with '@' whose line+2 begins with '+' (4-line records)
       while (p < len) {
         uint64_t q = p;
         int nl = 0;
@@ -225,40 +282,46 @@ extern "C" int pgo_count_feed_mt(pgo_counter* c, const char* text, uint64_t len,
     if (p < len && p > cuts.back()) cuts.push_back(p);
   }
   cuts.push_back(len);
-  size_t n = cuts.size() - 1;
-  std::vector<std::unordered_map<uint64_t, uint64_t>> part(n);
+  return cuts;
+}
+}  // namespace
+
+extern "C" int pgo_count_feed_mt(pgo_counter* c, const char* text, uint64_t len, int op, int threads) {
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  if (len == 0) return PG_OK;
+  if (text[0] != '>' && text[0] != '@') return fail(PG_ERR_FORMAT, "unsupported sequence format (expected '>' or '@')");
+  if (op != PG_OP_UPDATE) c->reserve(c->distinct.load() + len);  // every new key comes from one text byte
+  if (threads < 1) threads = 1;
+  if (len < (1u << 16)) threads = 1;
+  // chunks that do not start at the beginning of the file lack the leading header line the parser expects:
+  // each shard is parsed as its own file, which is valid because it starts at a record boundary.
+  std::vector<uint64_t> cuts = record_cuts(text, len, threads);
+  const size_t n = cuts.size() - 1;
   std::vector<int> status(n, PG_OK);
-  std::vector<std::thread> pool;
-  const auto& shared = c->table;
-  for (size_t t = 0; t < n; ++t) {
-    pool.emplace_back([&, t]() {
-      auto& mine = part[t];
-      auto sink = [&](uint64_t key) {
-        if (op == PG_OP_UPDATE) {
-          if (shared.find(key) != shared.end()) ++mine[key];
-        } else {
-          apply_op(mine, key, op);
-        }
-      };
-      KmerRoller<decltype(sink)> roller(c->k, sink);
-      status[t] = parse_records(text + cuts[t], cuts[t + 1] - cuts[t], [&](char ch) { roller(ch); });
-    });
+  std::vector<std::string> errs(n);
+  auto work = [&](size_t t) {
+    auto sink = [&](uint64_t key) { c->apply(key, op); };
+    KmerRoller<decltype(sink)> roller(c->k, sink);
+    status[t] = parse_records(text + cuts[t], cuts[t + 1] - cuts[t], [&](char ch) { roller(ch); });
+    if (status[t] != PG_OK) errs[t] = g_err;
+  };
+  if (n == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n; ++t) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
   }
-  for (auto& th : pool) th.join();
-  for (size_t t = 0; t < n; ++t) {
-    if (status[t] != PG_OK) return status[t];
-    for (auto& kv : part[t]) {
-      if (op == PG_OP_PRIME) c->table.emplace(kv.first, 0);
-      else c->table[kv.first] += kv.second;
-    }
-  }
+  for (size_t t = 0; t < n; ++t)
+    if (status[t] != PG_OK) return fail(status[t], errs[t]);
   return PG_OK;
 }
 
+extern "C" int pgo_count_feed(pgo_counter* c, const char* text, uint64_t len, int op) { return pgo_count_feed_mt(c, text, len, op, 1); }
+
 /* src/jellyfishcounter.cpp:26-49 (segments == NULL) and :51-85. */
-extern "C" pgo_counter* pgo_count_create_from_buffers(const char* reads, uint64_t reads_len,
-                                                      const char* segments, uint64_t segments_len,
-                                                      uint32_t k) {
+extern "C" pgo_counter* pgo_count_create_from_buffers(const char* reads, uint64_t reads_len, const char* segments,
+                                                      uint64_t segments_len, uint32_t k) {
   pgo_counter* c = pgo_count_new(k);
   if (!c) return nullptr;
   int st = PG_OK;
@@ -282,8 +345,7 @@ extern "C" int pgo_count_lookup_ascii(const pgo_counter* c, const char* kmers, u
     uint64_t code;
     out[i] = 0;
     if (!encode_ascii(kmers + i * c->k, c->k, &code)) continue;
-    auto it = c->table.find(canonical_of(code, c->k));
-    if (it != c->table.end()) out[i] = it->second;
+    out[i] = c->get(canonical_of(code, c->k));
   }
   return PG_OK;
 }
@@ -291,17 +353,15 @@ extern "C" int pgo_count_lookup_ascii(const pgo_counter* c, const char* kmers, u
 /* src/jellyfishcounter.cpp:97-104. */
 extern "C" int pgo_count_lookup(const pgo_counter* c, const uint64_t* kmers, uint64_t n, uint64_t* out) {
   if (!c) return fail(PG_ERR_ARG, "null counter");
-  for (uint64_t i = 0; i < n; ++i) {
-    auto it = c->table.find(canonical_of(kmers[i], c->k));
-    out[i] = it == c->table.end() ? 0 : it->second;
-  }
+  for (uint64_t i = 0; i < n; ++i) out[i] = c->get(canonical_of(kmers[i], c->k));
   return PG_OK;
 }
 
 /* src/jellyfishcounter.cpp:106-117. */
 extern "C" int pgo_count_kmer_coverage(const pgo_counter* c, uint64_t genome_kmers, uint64_t* out) {
   ld result = 0.0L, genome = 1.0L * genome_kmers;
-  for (auto& kv : c->table) result += (1.0L * kv.second) / genome;
+  for (uint64_t i = 0; i < c->cap; ++i)
+    if (c->keys[i].load(std::memory_order_relaxed) != pgo_counter::EMPTY) result += (1.0L * c->vals[i].load(std::memory_order_relaxed)) / genome;
   *out = (uint64_t)ceill(result);
   return PG_OK;
 }
@@ -309,8 +369,11 @@ extern "C" int pgo_count_kmer_coverage(const pgo_counter* c, uint64_t genome_kme
 /* src/jellyfishcounter.cpp:119-126 + src/histogram.cpp:26-30. */
 extern "C" int pgo_count_histogram(const pgo_counter* c, uint64_t max_count, uint64_t* bins) {
   std::fill(bins, bins + max_count + 1, 0);
-  for (auto& kv : c->table)
-    if (kv.second > 0 && kv.second <= max_count) ++bins[kv.second];
+  for (uint64_t i = 0; i < c->cap; ++i) {
+    if (c->keys[i].load(std::memory_order_relaxed) == pgo_counter::EMPTY) continue;
+    const uint64_t v = c->vals[i].load(std::memory_order_relaxed);
+    if (v > 0 && v <= max_count) ++bins[v];
+  }
   return PG_OK;
 }
 
@@ -375,7 +438,7 @@ extern "C" int pgo_count_compute_histogram(const pgo_counter* c, uint64_t max_co
   return PG_OK;
 }
 
-extern "C" uint64_t pgo_count_distinct(const pgo_counter* c) { return c ? c->table.size() : 0; }
+extern "C" uint64_t pgo_count_distinct(const pgo_counter* c) { return c ? c->distinct.load() : 0; }
 extern "C" void pgo_count_destroy(pgo_counter* c) { delete c; }
 
 /* =================================================================================================

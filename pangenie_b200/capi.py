@@ -96,6 +96,9 @@ class PgTimings(C.Structure):
         ("hmm_columns", C.c_uint64),
         ("hmm_block_launches", C.c_uint64),
         ("kernel_launches", C.c_uint64),
+        ("kmers_counted", C.c_uint64),
+        ("text_bytes", C.c_uint64),
+        ("prime_ms", C.c_double),
     ]
 
 
@@ -108,7 +111,8 @@ EXPORTS = [
     "pg_probtable_init", "pg_probtable_modify", "pg_probtable_get", "pg_probtable_free",
     "pg_result_layout", "pg_engine_create", "pg_engine_destroy", "pg_hmm_run", "pg_emission_run",
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
-    "pg_count_device_arrays", "pg_count_kmers_seen", "pg_count_last_ms",
+    "pg_count_device_arrays", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
+    "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch",
 ]
 
 
@@ -141,6 +145,7 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
             _sig(lib, p + "count_device_arrays", i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)])
             _sig(lib, p + "count_kmers_seen", u64, [vp])
             _sig(lib, p + "count_last_ms", dbl, [vp])
+            _sig(lib, p + "count_clear", i32, [vp])
         else:
             _sig(lib, p + "count_new", vp, [u32])
             _sig(lib, p + "count_create_from_buffers", vp, [vp, u64, vp, u64, u32])
@@ -168,6 +173,9 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "hmm_run", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgProbTable), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult)])
         _sig(lib, p + "emission_run", i32, [vp, C.POINTER(PgPanel), C.POINTER(PgProbTable), vp, vp, vp])
         _sig(lib, p + "fill_counts", i32, [vp, vp, u64, u32, C.POINTER(PgPanel)])
+        _sig(lib, p + "engine_load", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgHmmResult)])
+        _sig(lib, p + "engine_run_resident", i32, [vp, vp, u64, vp, u64, u32, u64, dbl, C.POINTER(PgHmmParams), C.POINTER(u64)])
+        _sig(lib, p + "engine_fetch", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgHmmResult)])
         _sig(lib, p + "genotype_run", i32, [vp, C.POINTER(PgGenotypeInput), u32, C.POINTER(PgPanel), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult), C.POINTER(u64)])
     else:
         # oracles: same data arguments, no engine handle

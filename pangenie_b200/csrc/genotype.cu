@@ -365,8 +365,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(FinalizeArgs a) {
       if (unique && best > 0.0) {
         g1 = (int16_t)b1;
         g2 = (int16_t)b2;
-        // prob_wrong = 1 - best in x87 has a 2^-64 grid; below half of it the reference sees exactly 0
-        gq = others > 2.7105054312137611e-20 ? (uint32_t)(-10.0 * log10(others)) : 10000u;
+        // prob_wrong = 1.0L - best: best (>= 1/2) sits on the x87 grid of 2^-64, so prob_wrong is a multiple of it
+        const double grid = best >= 0.5 ? 5.421010862427522e-20 : 2.710505431213761e-20;
+        const double wrong = rint(others / grid) * grid;
+        gq = wrong > 0.0 ? (uint32_t)(-10.0 * log10(wrong)) : 10000u;
       }
     }
     a.genotype[2 * v] = g1;
@@ -420,12 +422,14 @@ struct TileCfg {
 };
 
 static bool pick_cfg(uint32_t P, TileCfg& c) {
-  static const int cfgs[][3] = {{4, 3, 1}, {4, 5, 1}, {4, 9, 1}, {4, 17, 1}, {8, 17, 2}, {32, 9, 8}};
-  for (int i = 0; i < 6; ++i) {
+  // {lanes per row, columns per lane, rows per thread}; the first two run a whole chain in ONE warp
+  static const int cfgs[][3] = {{4, 2, 1}, {2, 8, 1}, {4, 5, 1}, {4, 9, 1}, {4, 17, 1}, {8, 17, 2}, {32, 9, 8}};
+  for (int i = 0; i < 7; ++i) {
     const int L = cfgs[i][0], CPL = cfgs[i][1], RPW = cfgs[i][2];
     const int rows_per_warp = (32 / L) * RPW;
     const int nw = ((int)P + rows_per_warp - 1) / rows_per_warp;
-    if (L * CPL >= (int)P && nw <= 32) {
+    const int max_warps = i < 2 ? 1 : 32;
+    if (L * CPL >= (int)P && nw <= max_warps) {
       c = {i, L, CPL, RPW, nw};
       return true;
     }
@@ -482,6 +486,7 @@ struct pg_engine {
   DevBuf<ChromCols> chroms;
   DevBuf<uint2> jobs;
   std::vector<uint8_t> h_is_column;
+  pg_counter* cached_counter = nullptr;  // reused across pg_engine_run_resident calls
 };
 
 static PanelDev panel_view(const pg_engine* e) {
@@ -517,6 +522,7 @@ extern "C" void pg_engine_destroy(pg_engine* e) {
   if (!e) return;
   {
     DeviceGuard g(e->device);
+    if (e->cached_counter) pg_count_destroy(e->cached_counter);
     if (e->stream) {
       cudaStreamSynchronize(e->stream);
       cudaStreamDestroy(e->stream);
@@ -634,7 +640,8 @@ static int engine_load_panels(pg_engine* e, uint32_t n_chrom, const pg_panel* pa
   if (need_counts) {
     std::vector<const uint16_t*> cov_src(n_chrom), cnt_src(n_chrom);
     for (uint32_t c = 0; c < n_chrom; ++c) {
-      if (panels[c].n_variants && (!panels[c].coverage || !panels[c].kmer_counts)) return fail(PG_ERR_ARG, "panel lacks kmer_counts / coverage");
+      const bool has_kmers = panels[c].n_variants && panels[c].kmer_offsets[panels[c].n_variants] > 0;
+      if (panels[c].n_variants && (!panels[c].coverage || (has_kmers && !panels[c].kmer_counts))) return fail(PG_ERR_ARG, "panel lacks kmer_counts / coverage");
       cov_src[c] = panels[c].coverage;
       cnt_src[c] = panels[c].kmer_counts;
     }
@@ -825,11 +832,12 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     int occ = 1;
 #define PG_OCC(L, CPL, RPW, NT) occ = occupancy_of<L, CPL, RPW, NT>();
     switch (cfg.id) {
-      case 0: PG_OCC(4, 3, 1, 64) break;
-      case 1: PG_OCC(4, 5, 1, 96) break;
-      case 2: PG_OCC(4, 9, 1, 160) break;
-      case 3: PG_OCC(4, 17, 1, 288) break;
-      case 4: PG_OCC(8, 17, 2, 544) break;
+      case 0: PG_OCC(4, 2, 1, 32) break;
+      case 1: PG_OCC(2, 8, 1, 32) break;
+      case 2: PG_OCC(4, 5, 1, 96) break;
+      case 3: PG_OCC(4, 9, 1, 160) break;
+      case 4: PG_OCC(4, 17, 1, 288) break;
+      case 5: PG_OCC(8, 17, 2, 544) break;
       default: PG_OCC(32, 9, 8, 1024) break;
     }
 #undef PG_OCC
@@ -843,11 +851,12 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
 #define PG_LAUNCH(L, CPL, RPW, NT, SK, BL) le = launch_pair<L, CPL, RPW, NT>(cp, e->n_chrom, grid_blocks, s, SK, BL);
 #define PG_DISPATCH(SK, BL)                                    \
     switch (cfg.id) {                                          \
-      case 0: PG_LAUNCH(4, 3, 1, 64, SK, BL) break;            \
-      case 1: PG_LAUNCH(4, 5, 1, 96, SK, BL) break;            \
-      case 2: PG_LAUNCH(4, 9, 1, 160, SK, BL) break;           \
-      case 3: PG_LAUNCH(4, 17, 1, 288, SK, BL) break;          \
-      case 4: PG_LAUNCH(8, 17, 2, 544, SK, BL) break;          \
+      case 0: PG_LAUNCH(4, 2, 1, 32, SK, BL) break;            \
+      case 1: PG_LAUNCH(2, 8, 1, 32, SK, BL) break;            \
+      case 2: PG_LAUNCH(4, 5, 1, 96, SK, BL) break;            \
+      case 3: PG_LAUNCH(4, 9, 1, 160, SK, BL) break;           \
+      case 4: PG_LAUNCH(4, 17, 1, 288, SK, BL) break;          \
+      case 5: PG_LAUNCH(8, 17, 2, 544, SK, BL) break;          \
       default: PG_LAUNCH(32, 9, 8, 1024, SK, BL) break;        \
     }
     if (need_skel) {
@@ -1021,6 +1030,8 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   pg_counter* c = pg_count_create_from_buffers(in->reads, in->reads_len, in->segments, in->segments_len, in->k, in->hash_size, e->device);
   if (!c) return last_code();
   e->tm.count_ms = c->last_feed_ms;
+  e->tm.kmers_counted = c->kmers_seen;
+  e->tm.text_bytes = in->reads_len;
   struct Guard {
     pg_counter* c;
     ~Guard() { pg_count_destroy(c); }
@@ -1044,4 +1055,76 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   PG_TRY(engine_fetch_results(e, n_chrom, panels, results));
   e->tm.kernel_launches = g_launches - l0;
   return PG_OK;
+}
+
+extern "C" int pg_engine_load(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_hmm_result* layouts) {
+  clear_error();
+  if (!e || !panels || !layouts) return fail(PG_ERR_ARG, "null argument");
+  return engine_load_panels(e, n_chrom, panels, layouts, false, true);
+}
+
+extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_t reads_len, const char* d_segments,
+                                      uint64_t segments_len, uint32_t k, uint64_t hash_size, double regularization,
+                                      const pg_hmm_params* params, uint64_t* kmer_abundance_peak) {
+  clear_error();
+  if (!e || !d_reads || !params) return fail(PG_ERR_ARG, "null argument");
+  if (!e->has_codes) return fail(PG_ERR_ARG, "call pg_engine_load first");
+  const uint64_t l0 = g_launches;
+  memset(&e->tm, 0, sizeof(e->tm));
+  const uint64_t max_distinct = d_segments ? std::max<uint64_t>(segments_len, 1024) : std::max<uint64_t>(hash_size, 1024);
+  if (e->cached_counter && (e->cached_counter->k != k || e->cached_counter->max_distinct < max_distinct)) {
+    pg_count_destroy(e->cached_counter);
+    e->cached_counter = nullptr;
+  }
+  if (!e->cached_counter) {
+    e->cached_counter = pg_count_new(k, max_distinct, e->device);
+    if (!e->cached_counter) return last_code();
+  } else {
+    PG_TRY(pg_count_clear(e->cached_counter));
+  }
+  pg_counter* c = e->cached_counter;
+  if (d_segments) {
+    PG_TRY(pg_count_feed_device(c, d_segments, segments_len, PG_OP_PRIME));
+    e->tm.prime_ms = c->last_feed_ms;
+    PG_TRY(pg_count_feed_device(c, d_reads, reads_len, PG_OP_UPDATE));
+  } else {
+    PG_TRY(pg_count_feed_device(c, d_reads, reads_len, PG_OP_COUNT));
+  }
+  e->tm.count_ms = c->last_feed_ms;
+  e->tm.kmers_counted = c->kmers_seen;
+  e->tm.text_bytes = reads_len;
+  uint64_t peak = 0;
+  cudaEvent_t h0, h1;
+  cudaEventCreate(&h0);
+  cudaEventCreate(&h1);
+  cudaEventRecord(h0, c->stream);
+  int st = pg_count_compute_histogram(c, 10000, d_segments != nullptr, nullptr, &peak);
+  cudaEventRecord(h1, c->stream);
+  cudaEventSynchronize(h1);
+  float hms = 0;
+  cudaEventElapsedTime(&hms, h0, h1);
+  cudaEventDestroy(h0);
+  cudaEventDestroy(h1);
+  if (st != PG_OK) return st;
+  if (kmer_abundance_peak) *kmer_abundance_peak = peak;
+  pg_probtable table;
+  PG_TRY(pg_probtable_init(&table, (uint16_t)(peak / 4), (uint16_t)(peak * 4), (uint16_t)(2 * peak), regularization));
+  struct TGuard {
+    pg_probtable* t;
+    ~TGuard() { pg_probtable_free(t); }
+  } tguard{&table};
+  PG_TRY(engine_fill(e, c, peak));
+  const double fill_ms = e->tm.fill_ms;
+  PG_TRY(engine_hmm(e, &table, params));
+  e->tm.fill_ms = fill_ms;
+  e->tm.histogram_ms = hms;
+  e->tm.kernel_launches = g_launches - l0;
+  return PG_OK;
+}
+
+extern "C" int pg_engine_fetch(pg_engine* e, uint32_t n_chrom, pg_panel* panels, pg_hmm_result* results) {
+  clear_error();
+  if (!e || !panels || !results) return fail(PG_ERR_ARG, "null argument");
+  PG_TRY(engine_fetch_counts(e, n_chrom, panels));
+  return engine_fetch_results(e, n_chrom, panels, results);
 }

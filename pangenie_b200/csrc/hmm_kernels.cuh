@@ -100,7 +100,7 @@ struct ChainSmem {
 // Register-resident chain.  L lanes per row, CPL columns per lane (interleaved: col = lc + s*L),
 // RPW rows per thread, G = 32/L rows per warp pass; warp w owns rows [w*RPW*G, (w+1)*RPW*G).
 // =================================================================================================
-template <int L, int CPL, int RPW>
+template <int L, int CPL, int RPW, bool ONEWARP = false>
 struct Chain {
   static constexpr int G = 32 / L;
   double x[RPW][CPL];
@@ -144,16 +144,21 @@ struct Chain {
   }
 
   // ---- descriptor ring: exactly one cp.async group per call, issued in column order ---------------
-  __device__ __forceinline__ void prefetch_desc(long long t, long long lo, long long hi) const {
+  // `slot` is the ring slot of column t: callers advance it incrementally (no division in the column loop)
+  __device__ __forceinline__ void prefetch_desc(int t, int lo, int hi, int slot) const {
     if (t >= lo && t < hi) {
-      const uint8_t* src = prm->desc + (size_t)t * prm->desc_stride;
-      uint8_t* dst = reinterpret_cast<uint8_t*>(sm->desc[(unsigned long long)t % HMM_NSLOT]);
+      const uint8_t* src = prm->desc + (size_t)(uint32_t)t * prm->desc_stride;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(sm->desc[slot]);
       for (uint32_t o = threadIdx.x * 16; o < prm->desc_stride; o += blockDim.x * 16) cp_async16(dst + o, src + o);
     }
     cp_async_commit();
   }
-  __device__ __forceinline__ const double* desc_d(long long t) const {
-    return reinterpret_cast<const double*>(sm->desc[(unsigned long long)t % HMM_NSLOT]);
+  __device__ __forceinline__ const double* desc_d(int slot) const { return reinterpret_cast<const double*>(sm->desc[slot]); }
+  static __device__ __forceinline__ int slot_next(int s) { return s + 1 == HMM_NSLOT ? 0 : s + 1; }
+  static __device__ __forceinline__ int slot_of(int t) { return (int)((uint32_t)t % (uint32_t)HMM_NSLOT); }
+  __device__ __forceinline__ void sync() const {
+    if (ONEWARP) __syncwarp();
+    else __syncthreads();
   }
 
   // ---- state I/O (dense row-major P x P doubles; each thread always touches the same cells) -------
@@ -209,9 +214,9 @@ struct Chain {
   // ---- one column.  FIRST: no transition (pre = 1).  WITH_POST: accumulate F o pre.  -----------------
   // Reads rs[cbuf] (row sums of x), writes rs[nbuf]; coefficients (t-1 -> t) forward, (t -> t+1) backward.
   template <bool BACKWARD, bool FIRST, bool WITH_POST>
-  __device__ __forceinline__ void step(long long t, int cbuf, int nbuf, double Tprev, const double* ucol,
+  __device__ __forceinline__ void step(int slot, int cbuf, int nbuf, double Tprev, const double* ucol,
                                        bool u_dead, int wbuf) {
-    const double* d = desc_d(t);
+    const double* d = desc_d(slot);
     const uint16_t* aidx = reinterpret_cast<const uint16_t*>(d + DESC_HEAD_DOUBLES);
     const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
     const double S = (double)P * (double)P;
@@ -278,8 +283,8 @@ struct Chain {
 
   // ---- posterior writer for a fast-A column whose class sums sit in wr[wbuf] (call after the barrier) ----
   // One warp: lane (alpha, beta) = (lane/4, lane%4) sums wr[beta][i] over rows i with allele index alpha.
-  __device__ __forceinline__ void write_posterior(long long t, int wbuf) {
-    const double* d = desc_d(t);
+  __device__ __forceinline__ void write_posterior(int slot, int wbuf) {
+    const double* d = desc_d(slot);
     const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
     if (A > HMM_FAST_A) return;
     const uint32_t alpha = lane >> 2, beta = lane & 3;
@@ -303,53 +308,85 @@ template <int L, int CPL, int RPW, int NT>
 __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
-  Chain<L, CPL, RPW> ch;
+  constexpr bool ONEWARP = NT == 32;
+  Chain<L, CPL, RPW, ONEWARP> ch;
   ch.init(sm, &p);
   const ChromCols cc = p.chroms[blockIdx.x];
-  const long long c0 = cc.col_begin, c1 = cc.col_end;
   if (cc.n_blocks <= 1) return;
-  const long long B = p.B;
+  const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
   const size_t PP = (size_t)p.P * p.P;
   constexpr int D = HMM_PREFETCH;
   int cur = 0;
   if (blockIdx.y == 0) {
-    // forward: needs F at columns c0 + k*B - 1 for k = 1 .. n_blocks-1
-    const long long last = c0 + (long long)(cc.n_blocks - 1) * B - 1;
-    for (int d = 0; d < D; ++d) ch.prefetch_desc(c0 + d, c0, c1);
+    // forward: needs F at columns c0 + k*B - 1 for k = 1 .. n_blocks-1 (stored as ckpt_fwd[k])
+    const int last = c0 + (int)(cc.n_blocks - 1) * B - 1;
+    int slot = ch.slot_of(c0), pslot = slot;
+    for (int d = 0; d < D; ++d) {
+      ch.prefetch_desc(c0 + d, c0, c1, pslot);
+      pslot = ch.slot_next(pslot);
+    }
     cp_async_wait<D - 1>();
-    __syncthreads();
-    ch.template step<false, true, false>(c0, 0, 0, 0.0, nullptr, false, 0);
-    ch.prefetch_desc(c0 + D, c0, c1);
+    ch.sync();
+    ch.template step<false, true, false>(slot, 0, 0, 0.0, nullptr, false, 0);
+    ch.prefetch_desc(c0 + D, c0, c1, pslot);
+    pslot = ch.slot_next(pslot);
     cp_async_wait<D - 1>();
-    __syncthreads();
-    for (long long t = c0 + 1; t <= last; ++t) {
-      if ((t - c0) % B == 0) ch.store_state(p.ckpt_fwd + (size_t)(cc.blk_begin + (t - c0) / B) * PP);
+    ch.sync();
+    slot = ch.slot_next(slot);
+    int until_ckpt = B - 1;  // columns to go before the state entering the next block is complete
+    uint32_t blk = cc.blk_begin + 1;
+    for (int t = c0 + 1; t <= last; ++t) {
+      if (until_ckpt == 0) {
+        ch.store_state(p.ckpt_fwd + (size_t)blk * PP);
+        ++blk;
+        until_ckpt = B;
+      }
+      --until_ckpt;
       const double T = ch.total(cur);
-      ch.template step<false, false, false>(t, cur, cur ^ 1, T, nullptr, false, 0);
-      ch.prefetch_desc(t + D, c0, c1);
+      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.prefetch_desc(t + D, c0, c1, pslot);
+      pslot = ch.slot_next(pslot);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
+      slot = ch.slot_next(slot);
       cur ^= 1;
     }
     ch.store_state(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * PP);
   } else {
-    // backward: needs Y at columns c0 + k*B for k = 1 .. n_blocks-1 (stored as ckpt_bwd[k-1])
-    const long long first = c0 + B;
-    for (int d = 0; d < D; ++d) ch.prefetch_desc(c1 - 1 - d, c0, c1);
+    // backward: needs Y at columns c0 + k*B for k = 1 .. n_blocks-1 (stored as ckpt_bwd[k-1]).
+    // The ring is walked downwards: slot(t-1) = slot(t) - 1 (mod NSLOT).
+    auto slot_prev = [](int s) { return s == 0 ? HMM_NSLOT - 1 : s - 1; };
+    const int first = c0 + B;
+    int slot = ch.slot_of(c1 - 1), pslot = slot;
+    for (int d = 0; d < D; ++d) {
+      ch.prefetch_desc(c1 - 1 - d, c0, c1, pslot);
+      pslot = slot_prev(pslot);
+    }
     cp_async_wait<D - 1>();
-    __syncthreads();
-    ch.template step<true, true, false>(c1 - 1, 0, 0, 0.0, nullptr, false, 0);
-    if ((c1 - 1 - c0) % B == 0) ch.store_state(p.ckpt_bwd + (size_t)(cc.blk_begin + (c1 - 1 - c0) / B - 1) * PP);
-    ch.prefetch_desc(c1 - 1 - D, c0, c1);
+    ch.sync();
+    ch.template step<true, true, false>(slot, 0, 0, 0.0, nullptr, false, 0);
+    int rel = (c1 - 1 - c0) % B;        // position of column t inside its block (one division per chain)
+    uint32_t blk = cc.blk_begin + (uint32_t)((c1 - 1 - c0) / B);
+    if (rel == 0) ch.store_state(p.ckpt_bwd + (size_t)(blk - 1) * PP);
+    ch.prefetch_desc(c1 - 1 - D, c0, c1, pslot);
+    pslot = slot_prev(pslot);
     cp_async_wait<D - 1>();
-    __syncthreads();
-    for (long long t = c1 - 2; t >= first; --t) {
+    ch.sync();
+    slot = slot_prev(slot);
+    for (int t = c1 - 2; t >= first; --t) {
+      if (rel == 0) {
+        rel = B;
+        --blk;
+      }
+      --rel;
       const double T = ch.total(cur);
-      ch.template step<true, false, false>(t, cur, cur ^ 1, T, nullptr, false, 0);
-      if ((t - c0) % B == 0) ch.store_state(p.ckpt_bwd + (size_t)(cc.blk_begin + (t - c0) / B - 1) * PP);
-      ch.prefetch_desc(t - D, c0, c1);
+      ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nullptr, false, 0);
+      if (rel == 0) ch.store_state(p.ckpt_bwd + (size_t)(blk - 1) * PP);
+      ch.prefetch_desc(t - D, c0, c1, pslot);
+      pslot = slot_prev(pslot);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
+      slot = slot_prev(slot);
       cur ^= 1;
     }
   }
@@ -364,52 +401,65 @@ __global__ void __launch_bounds__(NT) block_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
   __shared__ uint32_t s_job;
-  Chain<L, CPL, RPW> ch;
+  constexpr bool ONEWARP = NT == 32;
+  Chain<L, CPL, RPW, ONEWARP> ch;
   ch.init(sm, &p);
   const size_t PP = (size_t)p.P * p.P;
   double* buf = p.block_buf + (size_t)blockIdx.x * p.B * PP;
   constexpr int D = HMM_PREFETCH;
-  const int NW = NT / 32;
+  constexpr int NW = NT / 32;
+  auto slot_prev = [](int s) { return s == 0 ? HMM_NSLOT - 1 : s - 1; };
   while (true) {
-    __syncthreads();
+    ch.sync();
     if (threadIdx.x == 0) s_job = atomicAdd(p.work_counter, 1u);
-    __syncthreads();
+    ch.sync();
     const uint32_t job = s_job;
     if (job >= p.n_jobs) break;
     const uint2 jb = p.jobs[job];
     const ChromCols cc = p.chroms[jb.x];
-    const long long c0 = cc.col_begin, c1 = cc.col_end;
-    const long long cb = c0 + (long long)jb.y * p.B;
-    const long long ce = (cb + p.B < c1) ? cb + p.B : c1;
+    const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end;
+    const int cb = c0 + (int)jb.y * (int)p.B;
+    const int ce = (cb + (int)p.B < c1) ? cb + (int)p.B : c1;
     const uint32_t gblk = cc.blk_begin + jb.y;
     int cur = 0;
 
     // ---------------- forward sub-pass: F_t for t in [cb, ce) -> buf ----------------
-    for (int d = 0; d < D; ++d) ch.prefetch_desc(cb + d, cb, ce);
-    long long t = cb;
+    int slot = ch.slot_of(cb), pslot = slot;
+    for (int d = 0; d < D; ++d) {
+      ch.prefetch_desc(cb + d, cb, ce, pslot);
+      pslot = ch.slot_next(pslot);
+    }
+    int t = cb;
+    double* bcol = buf;
     if (jb.y == 0) {
       cp_async_wait<D - 1>();
-      __syncthreads();
-      ch.template step<false, true, false>(cb, 0, 0, 0.0, nullptr, false, 0);
-      ch.store_state(buf);
-      ch.prefetch_desc(cb + D, cb, ce);
+      ch.sync();
+      ch.template step<false, true, false>(slot, 0, 0, 0.0, nullptr, false, 0);
+      ch.store_state(bcol);
+      bcol += PP;
+      ch.prefetch_desc(cb + D, cb, ce, pslot);
+      pslot = ch.slot_next(pslot);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
+      slot = ch.slot_next(slot);
       t = cb + 1;
     } else {
       ch.load_state(p.ckpt_fwd + (size_t)gblk * PP);
       ch.publish_rowsums(0);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
     }
     for (; t < ce; ++t) {
       const double T = ch.total(cur);
       if (threadIdx.x == 0 && t > cb) sm->tf[t - 1 - cb] = T;
-      ch.template step<false, false, false>(t, cur, cur ^ 1, T, nullptr, false, 0);
-      ch.store_state(buf + (size_t)(t - cb) * PP);
-      ch.prefetch_desc(t + D, cb, ce);
+      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.store_state(bcol);
+      bcol += PP;
+      ch.prefetch_desc(t + D, cb, ce, pslot);
+      pslot = ch.slot_next(pslot);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
+      slot = ch.slot_next(slot);
       cur ^= 1;
     }
     {
@@ -417,45 +467,62 @@ __global__ void __launch_bounds__(NT) block_kernel(const ChainParams p) {
       if (threadIdx.x == 0) sm->tf[ce - 1 - cb] = T;
     }
     cp_async_wait<0>();
-    __syncthreads();
-    for (long long q = cb + threadIdx.x; q < ce; q += NT) p.tot_fwd[q] = sm->tf[q - cb];
+    ch.sync();
+    for (int q = cb + (int)threadIdx.x; q < ce; q += NT) p.tot_fwd[q] = sm->tf[q - cb];
 
     // ---------------- backward sub-pass with posterior ----------------
-    for (int d = 0; d < D; ++d) ch.prefetch_desc(ce - 1 - d, cb, ce);
+    slot = ch.slot_of(ce - 1);
+    pslot = slot;
+    for (int d = 0; d < D; ++d) {
+      ch.prefetch_desc(ce - 1 - d, cb, ce, pslot);
+      pslot = slot_prev(pslot);
+    }
     cur = 0;
     t = ce - 1;
-    long long pending = -1;  // column whose class sums await the posterior writer
+    bcol = buf + (size_t)(ce - 1 - cb) * PP;
+    int pending_slot = -1, pending_w = 0, pending_wbuf = 0;  // column whose class sums await the posterior writer
+    int wsel = 0, wbuf = 0;
     if (ce == c1) {
       cp_async_wait<D - 1>();
-      __syncthreads();
-      ch.template step<true, true, true>(t, 0, 0, 0.0, buf + (size_t)(t - cb) * PP, !(sm->tf[t - cb] > 0.0), (int)(t & 1));
-      ch.prefetch_desc(t - D, cb, ce);
+      ch.sync();
+      ch.template step<true, true, true>(slot, 0, 0, 0.0, bcol, !(sm->tf[t - cb] > 0.0), wbuf);
+      bcol -= PP;
+      ch.prefetch_desc(t - D, cb, ce, pslot);
+      pslot = slot_prev(pslot);
       cp_async_wait<D - 1>();
-      __syncthreads();
-      pending = t;
+      ch.sync();
+      pending_slot = slot; pending_w = wsel; pending_wbuf = wbuf;
+      wsel = wsel + 1 == NW ? 0 : wsel + 1;
+      wbuf ^= 1;
+      slot = slot_prev(slot);
       --t;
     } else {
       ch.load_state(p.ckpt_bwd + (size_t)gblk * PP);
       ch.publish_rowsums(0);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
     }
     for (; t >= cb; --t) {
-      if (pending >= 0 && ch.w == (int)(pending % NW)) ch.write_posterior(pending, (int)(pending & 1));
+      if (pending_slot >= 0 && ch.w == pending_w) ch.write_posterior(pending_slot, pending_wbuf);
       const double T = ch.total(cur);
       if (threadIdx.x == 0 && t + 1 < c1) p.tot_bwd[t + 1] = T;
       if (t - 2 >= cb) {  // pull the forward column needed two steps from now towards L2
-        const char* nxt = reinterpret_cast<const char*>(buf + (size_t)(t - 2 - cb) * PP);
+        const char* nxt = reinterpret_cast<const char*>(bcol - 2 * PP);
         for (size_t o = (size_t)threadIdx.x * 128; o < PP * 8; o += (size_t)NT * 128) prefetch_l2(nxt + o);
       }
-      ch.template step<true, false, true>(t, cur, cur ^ 1, T, buf + (size_t)(t - cb) * PP, !(sm->tf[t - cb] > 0.0), (int)(t & 1));
-      ch.prefetch_desc(t - D, cb, ce);
+      ch.template step<true, false, true>(slot, cur, cur ^ 1, T, bcol, !(sm->tf[t - cb] > 0.0), wbuf);
+      bcol -= PP;
+      ch.prefetch_desc(t - D, cb, ce, pslot);
+      pslot = slot_prev(pslot);
       cp_async_wait<D - 1>();
-      __syncthreads();
+      ch.sync();
+      pending_slot = slot; pending_w = wsel; pending_wbuf = wbuf;
+      wsel = wsel + 1 == NW ? 0 : wsel + 1;
+      wbuf ^= 1;
+      slot = slot_prev(slot);
       cur ^= 1;
-      pending = t;
     }
-    if (pending >= 0 && ch.w == (int)(pending % NW)) ch.write_posterior(pending, (int)(pending & 1));
+    if (pending_slot >= 0 && ch.w == pending_w) ch.write_posterior(pending_slot, pending_wbuf);
     {
       const double T = ch.total(cur);
       if (threadIdx.x == 0) p.tot_bwd[cb] = T;

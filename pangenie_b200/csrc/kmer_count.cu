@@ -908,3 +908,16 @@ extern "C" int pg_count_device_arrays(const pg_counter* c, uint64_t* keys_addr, 
 
 extern "C" uint64_t pg_count_kmers_seen(const pg_counter* c) { return c ? c->kmers_seen : 0; }
 extern "C" double pg_count_last_ms(const pg_counter* c) { return c ? c->last_feed_ms : 0.0; }
+
+extern "C" int pg_count_clear(pg_counter* c) {
+  clear_error();
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  DeviceGuard g(c->device);
+  fill_keys_kernel<<<1184, 512, 0, c->stream>>>(c->keys, c->capacity);
+  count_launch();
+  PG_CUDA(cudaMemsetAsync(c->counts, 0, c->capacity * sizeof(uint32_t), c->stream));
+  PG_CUDA(cudaMemsetAsync(c->d_scalars, 0, SC_N * sizeof(unsigned long long), c->stream));
+  PG_CUDA(cudaStreamSynchronize(c->stream));
+  c->kmers_seen = 0;
+  return PG_OK;
+}

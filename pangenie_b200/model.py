@@ -240,6 +240,36 @@ class Engine:
         _check(self._lib, self._lib.pg_genotype_run(self._h, C.byref(inp), len(panels), pa, C.byref(prm), ra, C.byref(peak)))
         return results, peak.value
 
+    def load(self, panels, results=None):
+        """Uploads the panels (incl. k-mer codes) to HBM; returns the Result buffers to fetch into."""
+        if results is None:
+            results = [Result(p) for p in panels]
+        self._resident = (panels, results)
+        pa = self._panel_array(panels)
+        ra = (PgHmmResult * len(panels))()
+        for i, r in enumerate(results):
+            ra[i] = r.as_struct()
+        _check(self._lib, self._lib.pg_engine_load(self._h, len(panels), pa, ra))
+        return results
+
+    def run_resident(self, d_reads, d_segments, k=31, hash_size=3_000_000_000, regularization=0.01, **kw) -> int:
+        """Whole stage from device-resident text (torch uint8 cuda tensors); returns the k-mer abundance peak."""
+        prm, _keep = hmm_params(**kw)
+        ra_, rl, _k1 = _bytes_arg(d_reads)
+        sa, sl, _k2 = _bytes_arg(d_segments)
+        peak = C.c_uint64(0)
+        _check(self._lib, self._lib.pg_engine_run_resident(self._h, ra_, rl, sa, sl, k, hash_size, regularization, C.byref(prm), C.byref(peak)))
+        return peak.value
+
+    def fetch(self):
+        panels, results = self._resident
+        pa = self._panel_array(panels)
+        ra = (PgHmmResult * len(panels))()
+        for i, r in enumerate(results):
+            ra[i] = r.as_struct()
+        _check(self._lib, self._lib.pg_engine_fetch(self._h, len(panels), pa, ra))
+        return results
+
     def timings(self) -> dict:
         t = PgTimings()
         _check(self._lib, self._lib.pg_engine_timings(self._h, C.byref(t)))

@@ -51,6 +51,11 @@ class Workload:
         return sum(len(c.positions) for c in self.chromosomes)
 
     @property
+    def record_bytes(self) -> int:
+        """Bytes of one (fixed-width) FASTQ record: '@' + 9 digits + LF, seq + LF, '+' LF, qual + LF."""
+        return 11 + self.read_len + 3 + self.read_len + 1
+
+    @property
     def panels(self):
         return [c.panel for c in self.chromosomes]
 

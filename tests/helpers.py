@@ -43,5 +43,10 @@ def assert_results_close(got, want, rtol=1e-6, atol=1e-12, check_gq=True, label=
     assert np.array_equal(got.coverage, want.coverage)
     if check_gq:
         # GQ = floor(-10 log10(1 - p)): allow +-1 where 1-p sits on an integer boundary within rounding
-        d = np.abs(got.quality.astype(np.int64) - want.quality.astype(np.int64))
-        assert d.max(initial=0) <= 1, f"{label}: GQ differs by {d.max()}"
+        # Above ~GQ 150 the reference's 1.0L - p is quantisation noise of the x87 grid (2^-64 = GQ 192.7), and
+        # 10000 is its value for an exact 0: there only the magnitude is comparable.
+        g, w = got.quality.astype(np.int64), want.quality.astype(np.int64)
+        lo = w < 150
+        d = np.abs(g - w)
+        assert d[lo].max(initial=0) <= 1, f"{label}: GQ differs by {d[lo].max()}"
+        assert (g[~lo] >= 140).all(), f"{label}: high-confidence GQ collapsed"

@@ -1,0 +1,107 @@
+"""GPU k-mer counter vs the CPU restatement of the jellyfish semantics (bit-exact: integer work)."""
+import numpy as np
+import pytest
+
+import pangenie_b200 as pg
+from pangenie_b200 import synth
+from tests import oracles
+
+pytestmark = pytest.mark.gpu
+
+
+def _codes(rng, n, k):
+    return rng.integers(0, 4 ** k if k < 32 else 2 ** 63, size=n, dtype=np.uint64)
+
+
+def _compare(oracle, reads, segments, k, probe_codes, hash_size=600_000):
+    g = pg.KmerCounter(reads, segments, k, hash_size=hash_size)
+    o = oracles.OracleCounter(oracle, reads, segments, k)
+    assert np.array_equal(g.histogram(300), o.histogram(300))
+    assert np.array_equal(g.lookup(probe_codes), o.lookup(probe_codes))
+    assert g.distinct() == o.distinct()
+    return g, o
+
+
+def test_reference_kmercounter_vectors(oracle):
+    # reference tests/KmerCounterTest.cpp:10-32 with tests/data/reads.fa and kmerfile.fa
+    reads = b">read1\nATGCTGTAAAAAAACGGC\n"
+    g = pg.KmerCounter(reads, None, 10, hash_size=1000)
+    seq = "ATGCTGTAAAAAAACGGC"
+    for i in range(len(seq) - 9):
+        assert g.getKmerAbundance(seq[i:i + 10]) == 1
+    kmerfile = b">kmers\nATGCTGTAAAA\n"
+    g2 = pg.KmerCounter(reads, kmerfile, 10, hash_size=1000)
+    assert g2.getKmerAbundance("ATGCTGTAAA") == 1 and g2.getKmerAbundance("TGCTGTAAAA") == 1
+    for i in range(2, len(seq) - 9):
+        assert g2.getKmerAbundance(seq[i:i + 10]) == 0
+    # canonical: the reverse complement of a counted k-mer has the same abundance
+    assert g.getKmerAbundance("TTTACAGCAT") == 1
+    assert g.getKmerAbundance("ATGCTGTAAN") == 0
+
+
+@pytest.mark.parametrize("k", [31, 21, 32, 5])
+def test_fastq_and_fasta_match_oracle(oracle, k):
+    rng = np.random.default_rng(k)
+    wl = synth.make_workload(n_chrom=2, n_variants=300, n_haplotypes=4, coverage=4.0, k=31, seed=k)
+    probes = np.concatenate([p.kmer_codes for p in wl.panels])[:5000] & np.uint64((1 << (2 * k)) - 1 if k < 32 else 0xFFFFFFFFFFFFFFFF)
+    probes = np.concatenate([probes, _codes(rng, 2000, k)])
+    _compare(oracle, wl.reads_fastq, wl.segments_fasta, k, probes)      # PRIME + UPDATE (default mode)
+    _compare(oracle, wl.reads_fastq[:400_000 // wl.record_bytes * wl.record_bytes], None, k, probes)  # count-all mode
+
+
+def test_edge_cases_match_oracle(oracle):
+    rng = np.random.default_rng(0)
+    probes = _codes(rng, 100, 7)
+    cases = [
+        b">a\nACGTACGTAC\n",                                   # shorter than k
+        b">a\nACGTNACGTACGTACGTNNACGTACGTACGT\n>b\nacgtacgtacgtacgt\n",   # N resets, lower case
+        b">a\nACGTACG\nTACGTACGT\n\nACGT\n>b\n>c\nAC\n",        # multi-line, empty line, empty records
+        b"@r1\nACGTACGTACGTAAAA\n+\n@@@@++++IIIIFFFF\n@r2\nTTTTTTTTTTTTTTTT\n+r2\n+@+@+@+@+@+@+@+@\n",  # '@'/'+' in quality
+        b"@r1\nAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA\n+\n" + b"F" * 68 + b"\n",  # homopolymer
+        b">a\nACGTACGTACGT",                                   # no trailing newline
+    ]
+    for text in cases:
+        for segs in (None, b">s\nACGTACGTACGTAAAATTTTTTTTTT\n"):
+            g = pg.KmerCounter(text, segs, 7, hash_size=10_000)
+            o = oracles.OracleCounter(oracle, text, segs, 7)
+            all7 = np.arange(4 ** 7, dtype=np.uint64)
+            assert np.array_equal(g.lookup(all7), o.lookup(all7)), (text[:30], segs)
+            assert np.array_equal(g.histogram(100), o.histogram(100))
+
+
+def test_tile_and_chunk_boundaries(oracle):
+    """Long multi-line FASTA records and reads crossing the 8064-byte tile advance."""
+    rng = np.random.default_rng(2)
+    seq = synth._ASCII[rng.integers(0, 4, size=300_000)]
+    fa = synth._fasta_record("chr", np.frombuffer(seq, np.uint8) if False else rng.integers(0, 4, size=300_000).astype(np.uint8), width=61)
+    probes = _codes(rng, 1000, 13)
+    g, o = _compare(oracle, fa, None, 13, probes)
+    all_codes = np.arange(4 ** 9, dtype=np.uint64)
+    g9 = pg.KmerCounter(fa, None, 9, hash_size=400_000)
+    o9 = oracles.OracleCounter(oracle, fa, None, 9)
+    assert np.array_equal(g9.lookup(all_codes), o9.lookup(all_codes))
+
+
+def test_incremental_feed_device_and_host_agree(oracle):
+    import torch
+    wl = synth.make_workload(n_chrom=1, n_variants=200, n_haplotypes=4, coverage=6.0, seed=3)
+    o = oracles.OracleCounter(oracle, wl.reads_fastq, wl.segments_fasta, 31)
+    g = pg.KmerCounter(None, None, 31, max_distinct=len(wl.segments_fasta))
+    g.feed(wl.segments_fasta, pg.PG_OP_PRIME)
+    rec = wl.record_bytes  # fixed-width FASTQ records: split the reads in two record-aligned shards
+    half = (len(wl.reads_fastq) // rec // 2) * rec
+    g.feed(torch.from_numpy(wl.reads_fastq[:half]).cuda(), pg.PG_OP_UPDATE)   # device-resident text
+    g.feed(wl.reads_fastq[half:], pg.PG_OP_UPDATE)                             # host text
+    probes = np.concatenate([p.kmer_codes for p in wl.panels])
+    assert np.array_equal(g.lookup(probes), o.lookup(probes))
+    assert np.array_equal(g.histogram(), o.histogram())
+    assert g.computeHistogram(10000, True) == o.computeHistogram(10000, True)
+    assert g.computeKmerCoverage(12345) == o.computeKmerCoverage(12345)
+
+
+def test_unsupported_inputs_fail_loudly():
+    with pytest.raises(pg.PgError):
+        pg.KmerCounter(b"ACGT\n", None, 3, hash_size=100)          # neither FASTA nor FASTQ
+    with pytest.raises(pg.PgError):
+        rng = np.random.default_rng(1)
+        pg.KmerCounter(synth._fasta_record("a", rng.integers(0, 4, size=40_000).astype(np.uint8)), None, 11, hash_size=10)  # count-all table too small

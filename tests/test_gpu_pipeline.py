@@ -1,0 +1,54 @@
+"""The `PanGenie -f` stage end to end through pg_genotype_run (host buffers) vs the oracle pipeline."""
+import numpy as np
+import pytest
+
+import pangenie_b200 as pg
+from pangenie_b200 import synth
+from tests import oracles
+from tests.helpers import assert_results_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pipeline(oracle, wl, regularization=0.01, **kw):
+    o = oracles.OracleCounter(oracle, wl.reads_fastq, wl.segments_fasta, wl.k)
+    peak = o.computeHistogram(10000, True)
+    o.fill_counts(peak, wl.panels)
+    table = pg.ProbabilityTable(peak // 4, peak * 4, 2 * peak, regularization)
+    return oracles.cpu_hmm_run(oracle, "pgo_", wl.panels, table, **kw), peak
+
+
+def test_genotype_run_matches_oracle_pipeline(engine, oracle, tmp_path):
+    wl = synth.make_workload(n_chrom=3, n_variants=1200, n_haplotypes=8, coverage=12.0, seed=21)
+    kw = dict(recombrate=1.26, effective_N=1e-5)
+    got, peak = engine.genotype_run(wl.reads_fastq, wl.segments_fasta, wl.panels, k=wl.k, histogram_path=str(tmp_path / "h.histo"), **kw)
+    counts_gpu = [p.kmer_counts.copy() for p in wl.panels]
+    cov_gpu = [p.coverage.copy() for p in wl.panels]
+    want, peak_o = _oracle_pipeline(oracle, wl, **kw)
+    assert peak == peak_o
+    for p, c, cv in zip(wl.panels, counts_gpu, cov_gpu):
+        assert np.array_equal(p.kmer_counts, c) and np.array_equal(p.coverage, cv)   # fill is bit-exact
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_results_close(g, w, label=f"chromosome {i}")
+    lines = open(tmp_path / "h.histo").read().splitlines()
+    assert len(lines) == 10002 and lines[-1].startswith("parameters\t")            # reference file format
+    t = engine.timings()
+    assert t["kernel_launches"] > 0 and t["hmm_columns"] > 0
+    # the simulated sample is mostly recovered
+    ok = tot = 0
+    for r, tr in zip(got, wl.truth):
+        ok += int((r.genotype.reshape(-1, 2) == np.sort(tr.astype(np.int16), axis=1)).all(axis=1).sum()); tot += len(tr)
+    assert ok / tot > 0.9
+
+
+def test_fill_counts_standalone(engine, oracle):
+    wl = synth.make_workload(n_chrom=2, n_variants=500, n_haplotypes=4, coverage=8.0, seed=22)
+    g = pg.KmerCounter(wl.reads_fastq, wl.segments_fasta, wl.k)
+    peak = g.computeHistogram(10000, True)
+    engine.fill_counts(g, peak, wl.panels)
+    got = [(p.kmer_counts.copy(), p.coverage.copy()) for p in wl.panels]
+    o = oracles.OracleCounter(oracle, wl.reads_fastq, wl.segments_fasta, wl.k)
+    assert o.computeHistogram(10000, True) == peak
+    o.fill_counts(peak, wl.panels)
+    for p, (c, cv) in zip(wl.panels, got):
+        assert np.array_equal(p.kmer_counts, c) and np.array_equal(p.coverage, cv)
