@@ -210,15 +210,20 @@ __global__ void __launch_bounds__(256) desc_build_kernel(PanelDev pd, const uint
     }
     uint16_t* aidx = reinterpret_cast<uint16_t*>(d + DESC_HEAD_DOUBLES);
     const uint32_t padded = (n_sel + 7u) & ~7u;
-    for (uint32_t q = lane; q < padded; q += 32) {
+    unsigned long long* bits = reinterpret_cast<unsigned long long*>(d + DESC_BITS_AT);
+    for (uint32_t q0 = 0; q0 < 320; q0 += 32) {  // 5 x 64 bits, zero beyond the selected paths
+      const uint32_t q = q0 + lane;
       uint16_t idx = 0;
       if (q < n_sel) {
         const uint16_t a = pd.path_to_allele[(size_t)v * pd.P + sel[q]];
         for (uint32_t i = 0; i < A; ++i)
           if (pd.allele_ids[ab + i] == a) idx = (uint16_t)i;
       }
-      aidx[q] = idx;
+      if (q < padded) aidx[q] = idx;
+      const unsigned b = __ballot_sync(0xffffffffu, (idx & 1u) != 0);
+      if (lane == 0) reinterpret_cast<unsigned*>(bits)[q0 >> 5] = b;
     }
+    if (lane == 0) d[31] = 0.0;
   }
 }
 
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(FinalizeArgs a) {
 // launch helpers: tile configuration by number of selected paths
 // -------------------------------------------------------------------------------------------------
 struct TileCfg {
-  int id, L, CPL, RPW, nwarps;
+  int id, L, CPL, RPW, nwarps, nthreads;
 };
 
 static bool pick_cfg(uint32_t P, TileCfg& c) {
@@ -429,8 +434,9 @@ static bool pick_cfg(uint32_t P, TileCfg& c) {
     const int rows_per_warp = (32 / L) * RPW;
     const int nw = ((int)P + rows_per_warp - 1) / rows_per_warp;
     const int max_warps = i < 2 ? 1 : 32;
-    if (L * CPL >= (int)P && nw <= max_warps) {
-      c = {i, L, CPL, RPW, nw};
+    static const int nts[] = {32, 32, 96, 160, 288, 544, 1024};
+    if (L * CPL >= (int)P && nw <= max_warps && nw * 32 <= nts[i]) {
+      c = {i, L, CPL, RPW, nw, nts[i]};
       return true;
     }
   }
@@ -784,7 +790,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   const uint32_t C = (uint32_t)col_variant.size();
   e->tm.hmm_columns = C;
   const uint32_t stride = (uint32_t)desc_bytes(P);
-  const size_t PP = (size_t)P * P;
+  const size_t PP = (size_t)cfg.CPL * cfg.RPW * cfg.nthreads;  // doubles per stored state (thread-major layout)
   PG_TRY(e->col_variant.reserve(std::max<uint32_t>(C, 1)));
   PG_TRY(e->col_cbeg.reserve(std::max<uint32_t>(C, 1)));
   PG_TRY(e->col_cend.reserve(std::max<uint32_t>(C, 1)));
@@ -823,6 +829,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     cudaEventRecord(e->ev[3], s);
 
     ChainParams cp;
+    cp.state_stride = (uint32_t)PP;
     cp.P = P; cp.B = B; cp.desc = e->desc.p; cp.desc_stride = stride; cp.chroms = e->chroms.p;
     cp.ckpt_fwd = e->ckpt_fwd.p; cp.ckpt_bwd = e->ckpt_bwd.p; cp.tot_fwd = e->tot_fwd.p; cp.tot_bwd = e->tot_bwd.p;
     cp.post = e->post.p; cp.gl_off = e->gl_off.p; cp.allele_off = e->allele_off.p; cp.allele_ids = e->allele_ids.p;

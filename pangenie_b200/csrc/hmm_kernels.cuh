@@ -27,7 +27,7 @@ namespace pg {
 
 constexpr int HMM_PMAX = 256;       // largest number of selected paths supported
 constexpr int HMM_RS_PAD = 288;     // row-sum array length in shared memory
-constexpr int HMM_NSLOT = 6;        // descriptor ring slots
+constexpr int HMM_NSLOT = 8;        // descriptor ring slots (power of two: slot = column & 7)
 constexpr int HMM_PREFETCH = 4;     // descriptor prefetch distance (columns)
 constexpr int HMM_FAST_A = 4;       // columns with <= 4 alleles: staged emission table + class sums
 constexpr int HMM_BMAX = 256;       // largest block length
@@ -36,8 +36,10 @@ constexpr int HMM_BMAX = 256;       // largest block length
 // doubles: [0..3] a,b,c,kappa of the transition (t-1 -> t); [4..7] the same for (t -> t+1);
 //          [8] header: u32 A (alleles), u32 variant index; [9] emission pointer (u64, A > HMM_FAST_A);
 //          [10..25] 4x4 emission table (row-major, allele-index space) when A <= HMM_FAST_A;
+//          [26..30] 5 x u64: bit p = allele index (0/1) of selected path p, for columns with A <= 2; [31] pad;
 // then u16 aidx[P] (allele index of each selected path), padded to 16 bytes.
-constexpr int DESC_HEAD_DOUBLES = 26;
+constexpr int DESC_HEAD_DOUBLES = 32;
+constexpr int DESC_BITS_AT = 26;
 __host__ __device__ inline size_t desc_bytes(uint32_t P) { return (size_t)DESC_HEAD_DOUBLES * 8 + (((size_t)P * 2 + 15) & ~(size_t)15); }
 constexpr int DESC_SLOT_WORDS = (DESC_HEAD_DOUBLES * 8 + 2 * HMM_PMAX + 16) / 8;
 
@@ -54,11 +56,12 @@ struct ChainParams {
   const uint8_t* desc;         // [n_cols] descriptor records
   uint32_t desc_stride;
   const ChromCols* chroms;     // [n_chrom]
-  double* ckpt_fwd;            // [n_blocks_total][P*P]  F of the column before block k (valid for k >= 1 in a chrom)
-  double* ckpt_bwd;            // [n_blocks_total][P*P]  Y of the column after block k (valid for k < n_blocks-1)
+  double* ckpt_fwd;            // [n_blocks_total][state_stride]  F of the column before block k (k >= 1 in a chrom)
+  double* ckpt_bwd;            // [n_blocks_total][state_stride]  Y of the column after block k (k < n_blocks-1)
   double* tot_fwd;             // [n_cols] TF_t = sum F_t
   double* tot_bwd;             // [n_cols] TY_t = sum Y_t
-  double* block_buf;           // [grid][B][P*P] forward columns of the block being processed
+  double* block_buf;           // [grid][B][state_stride] forward columns of the block being processed
+  uint32_t state_stride;       // doubles per stored state = cells per thread x threads (thread-major private layout)
   double* post;                // VCF-ordered raw posteriors (zero-initialised)
   const uint64_t* gl_off;      // [n_variants+1]
   const uint32_t* allele_off;  // [n_variants+1]
@@ -97,24 +100,26 @@ struct ChainSmem {
 };
 
 // =================================================================================================
-// Register-resident chain.  L lanes per row, CPL columns per lane (interleaved: col = lc + s*L),
+// Register-resident chain.  L lanes per row, each lane owns CPL CONTIGUOUS columns [lc*CPL, lc*CPL+CPL),
 // RPW rows per thread, G = 32/L rows per warp pass; warp w owns rows [w*RPW*G, (w+1)*RPW*G).
+// States are stored thread-major ([cell][thread]) so every warp access is a coalesced 256 B segment.
 // =================================================================================================
-template <int L, int CPL, int RPW, bool ONEWARP = false>
+template <int L, int CPL, int RPW, int NT>
 struct Chain {
   static constexpr int G = 32 / L;
+  static constexpr bool ONEWARP = NT == 32;
+  static constexpr int CELLS = RPW * CPL;
   double x[RPW][CPL];
   double rrow[RPW];
-  int w, lane, lr, lc;
+  int w, lane, lr, lc, col0;
   int P;
+  uint32_t vmask;  // bit s set <=> column col0+s < P
   ChainSmem* sm;
   const ChainParams* prm;
-  // posterior plumbing of the column being processed (multi-allelic general path)
   double* post_col;
   const uint16_t* ids_col;
 
   __device__ __forceinline__ int row(int r) const { return (w * RPW + r) * G + lr; }
-  __device__ __forceinline__ int col(int s) const { return lc + s * L; }
 
   __device__ __forceinline__ void init(ChainSmem* s, const ChainParams* p) {
     sm = s;
@@ -124,8 +129,17 @@ struct Chain {
     lane = threadIdx.x & 31;
     lr = lane / L;
     lc = lane % L;
+    col0 = lc * CPL;
+    int nv = P - col0;
+    nv = nv < 0 ? 0 : (nv > CPL ? CPL : nv);
+    vmask = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
     post_col = nullptr;
     ids_col = nullptr;
+  }
+
+  __device__ __forceinline__ void sync() const {
+    if (ONEWARP) __syncwarp();
+    else __syncthreads();
   }
 
   __device__ __forceinline__ double row_reduce(double v) const {
@@ -137,7 +151,9 @@ struct Chain {
   // total of the row sums in rs[buf]; every warp evaluates the same expression -> bitwise identical T
   __device__ __forceinline__ double total(int buf) const {
     double t = 0.0;
-    for (int i = lane; i < P; i += 32) t += sm->rs[buf][i];
+    constexpr int NR = (L * CPL + 31) / 32;  // rs[] is zero beyond P, so the trip count can be static
+#pragma unroll
+    for (int q = 0; q < NR; ++q) t += sm->rs[buf][lane + 32 * q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
@@ -149,44 +165,35 @@ struct Chain {
     if (t >= lo && t < hi) {
       const uint8_t* src = prm->desc + (size_t)(uint32_t)t * prm->desc_stride;
       uint8_t* dst = reinterpret_cast<uint8_t*>(sm->desc[slot]);
-      for (uint32_t o = threadIdx.x * 16; o < prm->desc_stride; o += blockDim.x * 16) cp_async16(dst + o, src + o);
+      for (uint32_t o = threadIdx.x * 16; o < prm->desc_stride; o += NT * 16) cp_async16(dst + o, src + o);
     }
     cp_async_commit();
   }
   __device__ __forceinline__ const double* desc_d(int slot) const { return reinterpret_cast<const double*>(sm->desc[slot]); }
-  static __device__ __forceinline__ int slot_next(int s) { return s + 1 == HMM_NSLOT ? 0 : s + 1; }
-  static __device__ __forceinline__ int slot_of(int t) { return (int)((uint32_t)t % (uint32_t)HMM_NSLOT); }
-  __device__ __forceinline__ void sync() const {
-    if (ONEWARP) __syncwarp();
-    else __syncthreads();
-  }
+  static __device__ __forceinline__ int slot_next(int s) { return (s + 1) & (HMM_NSLOT - 1); }
+  static __device__ __forceinline__ int slot_prev(int s) { return (s - 1) & (HMM_NSLOT - 1); }
+  static __device__ __forceinline__ int slot_of(int t) { return t & (HMM_NSLOT - 1); }
 
-  // ---- state I/O (dense row-major P x P doubles; each thread always touches the same cells) -------
+  // ---- state I/O: thread-major private layout, only valid cells touch memory ----------------------
   __device__ __forceinline__ void store_state(double* dst) const {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      const int i = row(r);
-      if (i < P) {
+      if (row(r) < P) {
 #pragma unroll
-        for (int s = 0; s < CPL; ++s) {
-          const int j = col(s);
-          if (j < P) dst[(size_t)i * P + j] = x[r][s];
-        }
+        for (int s = 0; s < CPL; ++s)
+          if ((vmask >> s) & 1u) dst[(size_t)(r * CPL + s) * NT + threadIdx.x] = x[r][s];
       }
     }
   }
   __device__ __forceinline__ void load_state(const double* src) {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      const int i = row(r);
+      const bool rok = row(r) < P;
 #pragma unroll
-      for (int s = 0; s < CPL; ++s) {
-        const int j = col(s);
-        x[r][s] = (i < P && j < P) ? src[(size_t)i * P + j] : 0.0;
-      }
+      for (int s = 0; s < CPL; ++s) x[r][s] = (rok && ((vmask >> s) & 1u)) ? src[(size_t)(r * CPL + s) * NT + threadIdx.x] : 0.0;
     }
   }
-  // publish the row sums of x into rs[buf]; caller must __syncthreads() before anyone reads them
+  // publish the row sums of x into rs[buf]; caller must sync() before anyone reads them
   __device__ __forceinline__ void publish_rowsums(int buf) {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
@@ -199,25 +206,25 @@ struct Chain {
     }
   }
 
-  __device__ __forceinline__ double emission(const double* d, uint32_t A, uint32_t ai, uint32_t aj) const {
-    if (A <= HMM_FAST_A) return d[10 + ai * HMM_FAST_A + aj];
-    const double* g = reinterpret_cast<const double*>(*reinterpret_cast<const unsigned long long*>(d + 9));
-    return __ldg(g + (size_t)ai * A + aj);
-  }
-
   __device__ __forceinline__ void bind_posterior(const double* d) {
     const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
     post_col = prm->post + prm->gl_off[v];
     ids_col = prm->allele_ids + prm->allele_off[v];
   }
 
-  // ---- one column.  FIRST: no transition (pre = 1).  WITH_POST: accumulate F o pre.  -----------------
+  // CPL bits of the 256-bit path mask starting at bit `start`
+  static __device__ __forceinline__ uint32_t bits_at(const unsigned long long* wds, int start) {
+    const int idx = start >> 6, sh = start & 63;
+    unsigned long long lo = wds[idx] >> sh;
+    if (sh) lo |= wds[idx + 1] << (64 - sh);  // 5 words are stored, so idx+1 is always readable
+    return (uint32_t)lo;
+  }
+
+  // ---- one column.  FIRST: no transition (pre = 1).  WITH_POST: accumulate F o pre (u = stored F_t). ----
   // Reads rs[cbuf] (row sums of x), writes rs[nbuf]; coefficients (t-1 -> t) forward, (t -> t+1) backward.
   template <bool BACKWARD, bool FIRST, bool WITH_POST>
-  __device__ __forceinline__ void step(int slot, int cbuf, int nbuf, double Tprev, const double* ucol,
-                                       bool u_dead, int wbuf) {
+  __device__ __forceinline__ void step(int slot, int cbuf, int nbuf, double Tprev, const double* ucol, bool u_dead, int wbuf) {
     const double* d = desc_d(slot);
-    const uint16_t* aidx = reinterpret_cast<const uint16_t*>(d + DESC_HEAD_DOUBLES);
     const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
     const double S = (double)P * (double)P;
     const bool dead = !FIRST && !(Tprev > 0.0);  // previous column underflowed -> uniform replacement
@@ -233,13 +240,70 @@ struct Chain {
         cc = BACKWARD ? 1.0 / S : d[o + 3] / S;
       }
     }
-    const bool fastA = A <= HMM_FAST_A;
-    if (WITH_POST && !fastA) bind_posterior(d);
     const double uni = 1.0 / S;
+    // the reference's backward cells of a dead column are all zero (hmm.cpp:348-352 with zero helpers)
+    const double wscale = dead ? 0.0 : 1.0;
+    double kap[CPL];
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) kap[s] = FIRST ? 0.0 : cb * sm->rs[cbuf][col0 + s];  // rs is zero-padded beyond P
+
+    if (A <= 2) {
+      // ------------- biallelic column: allele indices come as bitmasks, emission by select -------------
+      const unsigned long long* bw = reinterpret_cast<const unsigned long long*>(d + DESC_BITS_AT);
+      const uint32_t jb = bits_at(bw, col0);
+      const uint32_t m1 = jb & vmask, m0 = ~jb & vmask;
+      const double e00 = d[10], e01 = d[11], e10 = d[14], e11 = d[15];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int i = row(r);
+        const bool rok = i < P;
+        const uint32_t ib = rok ? (uint32_t)((bw[i >> 6] >> (i & 63)) & 1ull) : 0u;
+        const double er0 = rok ? (ib ? e10 : e00) : 0.0, er1 = rok ? (ib ? e11 : e01) : 0.0;
+        const double rho = FIRST ? 1.0 : cb * rrow[r] + cc;
+        double acc = 0.0, w0 = 0.0, w1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+          const double pre = FIRST ? 1.0 : fma(ca, x[r][s], rho + kap[s]);
+          const double em = ((m1 >> s) & 1u) ? er1 : (((m0 >> s) & 1u) ? er0 : 0.0);
+          if (WITH_POST) {
+            double uu = 0.0;
+            if (rok && ((vmask >> s) & 1u)) uu = u_dead ? uni : ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
+            const double wv = uu * pre * wscale;
+            w0 += ((m0 >> s) & 1u) ? wv : 0.0;  // accumulated separately: total - w1 would cancel
+            w1 += ((m1 >> s) & 1u) ? wv : 0.0;
+          }
+          const double v = pre * em;
+          x[r][s] = v;
+          acc += v;
+        }
+        acc = row_reduce(acc);
+        rrow[r] = acc;
+        if (lc == 0 && rok) sm->rs[nbuf][i] = acc;
+        if (WITH_POST) {
+          w0 = row_reduce(w0);
+          w1 = row_reduce(w1);
+          if (lc == 0 && rok) {
+            sm->wr[wbuf][0][i] = w0;
+            sm->wr[wbuf][1][i] = w1;
+            sm->wr[wbuf][2][i] = 0.0;
+            sm->wr[wbuf][3][i] = 0.0;
+            sm->wr_ai[wbuf][i] = (uint8_t)ib;
+          }
+        }
+      }
+      return;
+    }
+
+    // ------------- general column (A > 2): emission by table lookup -------------
+    const uint16_t* aidx = reinterpret_cast<const uint16_t*>(d + DESC_HEAD_DOUBLES);
+    const bool fastA = A <= HMM_FAST_A;
+    const double* eg = reinterpret_cast<const double*>(*reinterpret_cast<const unsigned long long*>(d + 9));
+    if (WITH_POST && !fastA) bind_posterior(d);
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int i = row(r);
-      const uint32_t ai = i < P ? aidx[i] : 0;
+      const bool rok = i < P;
+      const uint32_t ai = rok ? aidx[i] : 0;
       const double rho = FIRST ? 1.0 : cb * rrow[r] + cc;
       double acc = 0.0;
       double wc[HMM_FAST_A];
@@ -247,15 +311,13 @@ struct Chain {
       for (int q = 0; q < HMM_FAST_A; ++q) wc[q] = 0.0;
 #pragma unroll
       for (int s = 0; s < CPL; ++s) {
-        const int j = col(s);
-        const bool ok = i < P && j < P;
-        const uint32_t aj = j < P ? aidx[j] : 0;
-        const double pre = FIRST ? 1.0 : fma(ca, x[r][s], rho + (j < P ? cb * sm->rs[cbuf][j] : 0.0));
+        const bool ok = rok && ((vmask >> s) & 1u);
+        const uint32_t aj = ok ? aidx[col0 + s] : 0;
+        const double pre = FIRST ? 1.0 : fma(ca, x[r][s], rho + kap[s]);
         if (WITH_POST) {
-          // the reference's backward cells of a dead column are all zero (hmm.cpp:348-352 with zero helpers)
           double uu = 0.0;
-          if (ok) uu = u_dead ? uni : ucol[(size_t)i * P + j];
-          const double wv = (ok && !dead) ? uu * pre : 0.0;
+          if (ok) uu = u_dead ? uni : ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
+          const double wv = uu * pre * wscale;
           if (fastA) {
 #pragma unroll
             for (int q = 0; q < HMM_FAST_A; ++q) wc[q] += (aj == (uint32_t)q) ? wv : 0.0;
@@ -263,20 +325,22 @@ struct Chain {
             atomicAdd(post_col + pair_index(ids_col[ai], ids_col[aj]), wv);  // rare general path
           }
         }
-        const double v = ok ? pre * emission(d, A, ai, aj) : 0.0;
+        double em = 0.0;
+        if (ok) em = fastA ? d[10 + ai * HMM_FAST_A + aj] : __ldg(eg + (size_t)ai * A + aj);
+        const double v = pre * em;
         x[r][s] = v;
         acc += v;
       }
       acc = row_reduce(acc);
       rrow[r] = acc;
-      if (lc == 0 && i < P) sm->rs[nbuf][i] = acc;
+      if (lc == 0 && rok) sm->rs[nbuf][i] = acc;
       if (WITH_POST && fastA) {
 #pragma unroll
         for (int q = 0; q < HMM_FAST_A; ++q) {
           const double c = row_reduce(wc[q]);
-          if (lc == 0 && i < P) sm->wr[wbuf][q][i] = c;
+          if (lc == 0 && rok) sm->wr[wbuf][q][i] = c;
         }
-        if (lc == 0 && i < P) sm->wr_ai[wbuf][i] = (uint8_t)ai;
+        if (lc == 0 && rok) sm->wr_ai[wbuf][i] = (uint8_t)ai;
       }
     }
   }
@@ -308,13 +372,14 @@ template <int L, int CPL, int RPW, int NT>
 __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
-  constexpr bool ONEWARP = NT == 32;
-  Chain<L, CPL, RPW, ONEWARP> ch;
+  Chain<L, CPL, RPW, NT> ch;
   ch.init(sm, &p);
   const ChromCols cc = p.chroms[blockIdx.x];
   if (cc.n_blocks <= 1) return;
+  for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;  // zero padding beyond P
+  ch.sync();
   const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
-  const size_t PP = (size_t)p.P * p.P;
+  const size_t PP = p.state_stride;
   constexpr int D = HMM_PREFETCH;
   int cur = 0;
   if (blockIdx.y == 0) {
@@ -355,7 +420,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
   } else {
     // backward: needs Y at columns c0 + k*B for k = 1 .. n_blocks-1 (stored as ckpt_bwd[k-1]).
     // The ring is walked downwards: slot(t-1) = slot(t) - 1 (mod NSLOT).
-    auto slot_prev = [](int s) { return s == 0 ? HMM_NSLOT - 1 : s - 1; };
+    auto slot_prev = [](int s) { return (s - 1) & (HMM_NSLOT - 1); };
     const int first = c0 + B;
     int slot = ch.slot_of(c1 - 1), pslot = slot;
     for (int d = 0; d < D; ++d) {
@@ -397,18 +462,18 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
 // phase 2: block forward-backward with fused posterior.  Persistent CTAs pull (chromosome, block) jobs.
 // -------------------------------------------------------------------------------------------------
 template <int L, int CPL, int RPW, int NT>
-__global__ void __launch_bounds__(NT) block_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
   __shared__ uint32_t s_job;
-  constexpr bool ONEWARP = NT == 32;
-  Chain<L, CPL, RPW, ONEWARP> ch;
+  Chain<L, CPL, RPW, NT> ch;
   ch.init(sm, &p);
-  const size_t PP = (size_t)p.P * p.P;
+  for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;  // zero padding beyond P
+  const size_t PP = p.state_stride;
   double* buf = p.block_buf + (size_t)blockIdx.x * p.B * PP;
   constexpr int D = HMM_PREFETCH;
   constexpr int NW = NT / 32;
-  auto slot_prev = [](int s) { return s == 0 ? HMM_NSLOT - 1 : s - 1; };
+  auto slot_prev = [](int s) { return (s - 1) & (HMM_NSLOT - 1); };
   while (true) {
     ch.sync();
     if (threadIdx.x == 0) s_job = atomicAdd(p.work_counter, 1u);
