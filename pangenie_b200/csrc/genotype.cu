@@ -428,7 +428,7 @@ struct TileCfg {
 
 static bool pick_cfg(uint32_t P, TileCfg& c) {
   // {lanes per row, columns per lane, rows per thread}; the first two run a whole chain in ONE warp
-  static const int cfgs[][3] = {{4, 2, 1}, {2, 8, 1}, {4, 5, 1}, {4, 9, 1}, {4, 17, 1}, {8, 17, 2}, {32, 9, 8}};
+  static const int cfgs[][3] = {{1, 9, 1}, {1, 16, 1}, {4, 5, 1}, {4, 9, 1}, {4, 17, 1}, {8, 17, 2}, {32, 9, 8}};
   for (int i = 0; i < 7; ++i) {
     const int L = cfgs[i][0], CPL = cfgs[i][1], RPW = cfgs[i][2];
     const int rows_per_warp = (32 / L) * RPW;
@@ -839,8 +839,8 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     int occ = 1;
 #define PG_OCC(L, CPL, RPW, NT) occ = occupancy_of<L, CPL, RPW, NT>();
     switch (cfg.id) {
-      case 0: PG_OCC(4, 2, 1, 32) break;
-      case 1: PG_OCC(2, 8, 1, 32) break;
+      case 0: PG_OCC(1, 9, 1, 32) break;
+      case 1: PG_OCC(1, 16, 1, 32) break;
       case 2: PG_OCC(4, 5, 1, 96) break;
       case 3: PG_OCC(4, 9, 1, 160) break;
       case 4: PG_OCC(4, 17, 1, 288) break;
@@ -858,8 +858,8 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
 #define PG_LAUNCH(L, CPL, RPW, NT, SK, BL) le = launch_pair<L, CPL, RPW, NT>(cp, e->n_chrom, grid_blocks, s, SK, BL);
 #define PG_DISPATCH(SK, BL)                                    \
     switch (cfg.id) {                                          \
-      case 0: PG_LAUNCH(4, 2, 1, 32, SK, BL) break;            \
-      case 1: PG_LAUNCH(2, 8, 1, 32, SK, BL) break;            \
+      case 0: PG_LAUNCH(1, 9, 1, 32, SK, BL) break;            \
+      case 1: PG_LAUNCH(1, 16, 1, 32, SK, BL) break;           \
       case 2: PG_LAUNCH(4, 5, 1, 96, SK, BL) break;            \
       case 3: PG_LAUNCH(4, 9, 1, 160, SK, BL) break;           \
       case 4: PG_LAUNCH(4, 17, 1, 288, SK, BL) break;          \

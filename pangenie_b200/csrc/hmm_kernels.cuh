@@ -150,6 +150,16 @@ struct Chain {
 
   // total of the row sums in rs[buf]; every warp evaluates the same expression -> bitwise identical T
   __device__ __forceinline__ double total(int buf) const {
+    if (L == 1) {  // lane-per-row layout: all CPL row sums are read by every lane anyway; same order in all lanes
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int q = 0; q + 1 < CPL; q += 2) {
+        t0 += sm->rs[buf][q];
+        t1 += sm->rs[buf][q + 1];
+      }
+      if (CPL & 1) t0 += sm->rs[buf][CPL - 1];
+      return t0 + t1;
+    }
     double t = 0.0;
     constexpr int NR = (L * CPL + 31) / 32;  // rs[] is zero beyond P, so the trip count can be static
 #pragma unroll
@@ -162,12 +172,14 @@ struct Chain {
   // ---- descriptor ring: exactly one cp.async group per call, issued in column order ---------------
   // `slot` is the ring slot of column t: callers advance it incrementally (no division in the column loop)
   __device__ __forceinline__ void prefetch_desc(int t, int lo, int hi, int slot) const {
-    if (t >= lo && t < hi) {
-      const uint8_t* src = prm->desc + (size_t)(uint32_t)t * prm->desc_stride;
-      uint8_t* dst = reinterpret_cast<uint8_t*>(sm->desc[slot]);
-      for (uint32_t o = threadIdx.x * 16; o < prm->desc_stride; o += NT * 16) cp_async16(dst + o, src + o);
+    if (w == 0) {  // one warp moves the record (<= 752 B = 47 x 16 B); the column barrier publishes it
+      if (t >= lo && t < hi) {
+        const uint8_t* src = prm->desc + (size_t)(uint32_t)t * prm->desc_stride;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(sm->desc[slot]);
+        for (uint32_t o = lane * 16; o < prm->desc_stride; o += 32 * 16) cp_async16(dst + o, src + o);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   }
   __device__ __forceinline__ const double* desc_d(int slot) const { return reinterpret_cast<const double*>(sm->desc[slot]); }
   static __device__ __forceinline__ int slot_next(int s) { return (s + 1) & (HMM_NSLOT - 1); }
@@ -243,15 +255,14 @@ struct Chain {
     const double uni = 1.0 / S;
     // the reference's backward cells of a dead column are all zero (hmm.cpp:348-352 with zero helpers)
     const double wscale = dead ? 0.0 : 1.0;
-    double kap[CPL];
+    double rj[CPL];  // row sums of my columns (rs is zero-padded beyond P)
 #pragma unroll
-    for (int s = 0; s < CPL; ++s) kap[s] = FIRST ? 0.0 : cb * sm->rs[cbuf][col0 + s];  // rs is zero-padded beyond P
+    for (int s = 0; s < CPL; ++s) rj[s] = FIRST ? 0.0 : sm->rs[cbuf][col0 + s];
 
     if (A <= 2) {
       // ------------- biallelic column: allele indices come as bitmasks, emission by select -------------
       const unsigned long long* bw = reinterpret_cast<const unsigned long long*>(d + DESC_BITS_AT);
       const uint32_t jb = bits_at(bw, col0);
-      const uint32_t m1 = jb & vmask, m0 = ~jb & vmask;
       const double e00 = d[10], e01 = d[11], e10 = d[14], e11 = d[15];
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
@@ -260,22 +271,27 @@ struct Chain {
         const uint32_t ib = rok ? (uint32_t)((bw[i >> 6] >> (i & 63)) & 1ull) : 0u;
         const double er0 = rok ? (ib ? e10 : e00) : 0.0, er1 = rok ? (ib ? e11 : e01) : 0.0;
         const double rho = FIRST ? 1.0 : cb * rrow[r] + cc;
-        double acc = 0.0, w0 = 0.0, w1 = 0.0;
+        double acc = 0.0, acc2 = 0.0, w0 = 0.0, w1 = 0.0;
 #pragma unroll
         for (int s = 0; s < CPL; ++s) {
-          const double pre = FIRST ? 1.0 : fma(ca, x[r][s], rho + kap[s]);
-          const double em = ((m1 >> s) & 1u) ? er1 : (((m0 >> s) & 1u) ? er0 : 0.0);
+          const bool ok = (vmask >> s) & 1u;  // lane-constant; selects only, no branches in the cell body
+          const bool c1 = (jb >> s) & 1u;
+          const double pre = FIRST ? 1.0 : fma(ca, x[r][s], fma(cb, rj[s], rho));
           if (WITH_POST) {
             double uu = 0.0;
-            if (rok && ((vmask >> s) & 1u)) uu = u_dead ? uni : ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
+            if (ok && rok) uu = ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
+            if (u_dead) uu = (ok && rok) ? uni : 0.0;
             const double wv = uu * pre * wscale;
-            w0 += ((m0 >> s) & 1u) ? wv : 0.0;  // accumulated separately: total - w1 would cancel
-            w1 += ((m1 >> s) & 1u) ? wv : 0.0;
+            w0 += c1 ? 0.0 : wv;  // accumulated separately: total - w1 would cancel
+            w1 += c1 ? wv : 0.0;
           }
-          const double v = pre * em;
+          const double pe = pre * (c1 ? er1 : er0);
+          const double v = ok ? pe : 0.0;
           x[r][s] = v;
-          acc += v;
+          if (s & 1) acc2 += v;
+          else acc += v;
         }
+        acc += acc2;
         acc = row_reduce(acc);
         rrow[r] = acc;
         if (lc == 0 && rok) sm->rs[nbuf][i] = acc;
@@ -313,7 +329,7 @@ struct Chain {
       for (int s = 0; s < CPL; ++s) {
         const bool ok = rok && ((vmask >> s) & 1u);
         const uint32_t aj = ok ? aidx[col0 + s] : 0;
-        const double pre = FIRST ? 1.0 : fma(ca, x[r][s], rho + kap[s]);
+        const double pre = FIRST ? 1.0 : fma(ca, x[r][s], fma(cb, rj[s], rho));
         if (WITH_POST) {
           double uu = 0.0;
           if (ok) uu = u_dead ? uni : ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
