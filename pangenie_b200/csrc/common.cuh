@@ -84,12 +84,18 @@ __device__ __forceinline__ uint64_t revcomp_2bit(uint64_t x, uint32_t k) {
 }
 
 __device__ __forceinline__ uint64_t hash_kmer(uint64_t h) {
-  h ^= h >> 33;
-  h *= 0xff51afd7ed558ccdULL;
-  h ^= h >> 33;
-  h *= 0xc4ceb9fe1a85ec53ULL;
-  h ^= h >> 33;
+  h *= 0x9E3779B97F4A7C15ULL;
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ULL;
+  h ^= h >> 32;
   return h;
+}
+
+/** Home slot in a table of capacity q << sh (q < 2^32): high hash word scaled by q, low hash bits below. */
+__device__ __forceinline__ uint64_t home_slot(uint64_t kmer, uint32_t q, uint32_t sh) {
+  const uint64_t h = hash_kmer(kmer);
+  const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
+  return ((uint64_t)__umulhi(hi, q) << sh) | (uint64_t)(lo & ((1u << sh) - 1u));
 }
 
 constexpr uint64_t EMPTY_KEY = ~0ULL;  // never a canonical k-mer for k <= 32 (all-T canonicalises to all-A)
@@ -100,7 +106,8 @@ constexpr uint64_t EMPTY_KEY = ~0ULL;  // never a canonical k-mer for k <= 32 (a
 struct pg_counter {
   int device = 0;
   uint32_t k = 0;
-  uint64_t capacity = 0;      // slots
+  uint64_t capacity = 0;      // slots = cap_q << cap_sh
+  uint32_t cap_q = 0, cap_sh = 0;
   uint64_t max_distinct = 0;  // keys the caller asked room for
   uint64_t* keys = nullptr;   // [capacity] canonical k-mer or EMPTY_KEY
   uint32_t* counts = nullptr; // [capacity]

@@ -231,10 +231,10 @@ __global__ void __launch_bounds__(256) desc_build_kernel(PanelDev pd, const uint
 // fill (src/commands.cpp:113-137, src/kmerparser.cpp:30-49)
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t table_lookup_dev(uint64_t code, uint32_t k, const uint64_t* __restrict__ keys,
-                                                     const uint32_t* __restrict__ counts, uint64_t cap) {
+                                                     const uint32_t* __restrict__ counts, uint64_t cap, uint32_t q, uint32_t sh) {
   const uint64_t rc = revcomp_2bit(code, k);
   const uint64_t can = code < rc ? code : rc;
-  uint64_t slot = __umul64hi(hash_kmer(can), cap);
+  uint64_t slot = home_slot(can, q, sh);
   for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
     const uint64_t cur = keys[slot];
     if (cur == can) return counts[slot];
@@ -246,20 +246,20 @@ __device__ __forceinline__ uint32_t table_lookup_dev(uint64_t code, uint32_t k, 
 
 __global__ void __launch_bounds__(256) fill_kmer_counts_kernel(const uint64_t* __restrict__ codes, uint64_t n, uint32_t k,
                                                                 const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
-                                                                uint64_t cap, uint16_t* __restrict__ out) {
+                                                                uint64_t cap, uint32_t q, uint32_t sh, uint16_t* __restrict__ out) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    out[i] = (uint16_t)table_lookup_dev(codes[i], k, keys, counts, cap);  // size_t -> unsigned short (commands.cpp:118,130)
+    out[i] = (uint16_t)table_lookup_dev(codes[i], k, keys, counts, cap, q, sh);  // size_t -> unsigned short (commands.cpp:118,130)
 }
 
 __global__ void __launch_bounds__(256) fill_coverage_kernel(const uint32_t* __restrict__ flank_off, const uint64_t* __restrict__ flank_codes,
                                                              uint32_t V, uint32_t k, const uint64_t* __restrict__ keys,
-                                                             const uint32_t* __restrict__ counts, uint64_t cap, uint64_t peak,
-                                                             uint16_t* __restrict__ coverage) {
+                                                             const uint32_t* __restrict__ counts, uint64_t cap, uint32_t q, uint32_t sh,
+                                                             uint64_t peak, uint16_t* __restrict__ coverage) {
   const uint64_t min_cov = peak / 4, max_cov = peak * 4;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
     uint64_t total_cov = 0, total_kmers = 0;
     for (uint32_t f = flank_off[v]; f < flank_off[v + 1]; ++f) {
-      const uint64_t c = table_lookup_dev(flank_codes[f], k, keys, counts, cap);
+      const uint64_t c = table_lookup_dev(flank_codes[f], k, keys, counts, cap, q, sh);
       if (c < min_cov || c > max_cov) continue;
       total_cov += c;
       total_kmers += 1;
@@ -935,12 +935,12 @@ static int engine_fill(pg_engine* e, const pg_counter* c, uint64_t peak) {
   cudaEventRecord(e->ev[8], s);
   if (e->K) {
     const int grid = (int)std::min<uint64_t>((e->K + 255) / 256, (uint64_t)e->sm_count * 16);
-    fill_kmer_counts_kernel<<<grid, 256, 0, s>>>(e->kmer_codes.p, e->K, c->k, c->keys, c->counts, c->capacity, e->kmer_counts.p);
+    fill_kmer_counts_kernel<<<grid, 256, 0, s>>>(e->kmer_codes.p, e->K, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, e->kmer_counts.p);
     count_launch();
   }
   if (e->V) {
     const int grid = (int)std::min<uint64_t>(((uint64_t)e->V + 255) / 256, (uint64_t)e->sm_count * 16);
-    fill_coverage_kernel<<<grid, 256, 0, s>>>(e->flank_off.p, e->flank_codes.p, e->V, c->k, c->keys, c->counts, c->capacity, peak, e->coverage.p);
+    fill_coverage_kernel<<<grid, 256, 0, s>>>(e->flank_off.p, e->flank_codes.p, e->V, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, peak, e->coverage.p);
     count_launch();
   }
   PG_CUDA(cudaGetLastError());
@@ -1033,16 +1033,29 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   if (!e || !in || !panels || !params || !results) return fail(PG_ERR_ARG, "null argument");
   const uint64_t l0 = g_launches;
   memset(&e->tm, 0, sizeof(e->tm));
-  // 1) count (src/commands.cpp:829-833)
-  pg_counter* c = pg_count_create_from_buffers(in->reads, in->reads_len, in->segments, in->segments_len, in->k, in->hash_size, e->device);
-  if (!c) return last_code();
+  // 1) count (src/commands.cpp:829-833); the table and its staging buffers are kept across calls
+  const uint64_t max_distinct = in->segments ? std::max<uint64_t>(in->segments_len, 1024) : std::max<uint64_t>(in->hash_size, 1024);
+  if (e->cached_counter && (e->cached_counter->k != in->k || e->cached_counter->max_distinct < max_distinct)) {
+    pg_count_destroy(e->cached_counter);
+    e->cached_counter = nullptr;
+  }
+  if (!e->cached_counter) {
+    e->cached_counter = pg_count_new(in->k, max_distinct, e->device);
+    if (!e->cached_counter) return last_code();
+  } else {
+    PG_TRY(pg_count_clear(e->cached_counter));
+  }
+  pg_counter* c = e->cached_counter;
+  if (in->segments) {
+    PG_TRY(pg_count_feed(c, in->segments, in->segments_len, PG_OP_PRIME));
+    e->tm.prime_ms = c->last_feed_ms;
+    PG_TRY(pg_count_feed(c, in->reads, in->reads_len, PG_OP_UPDATE));
+  } else {
+    PG_TRY(pg_count_feed(c, in->reads, in->reads_len, PG_OP_COUNT));
+  }
   e->tm.count_ms = c->last_feed_ms;
   e->tm.kmers_counted = c->kmers_seen;
   e->tm.text_bytes = in->reads_len;
-  struct Guard {
-    pg_counter* c;
-    ~Guard() { pg_count_destroy(c); }
-  } guard{c};
   // 2) histogram peak (:840); largest_peak == count_only_graph
   uint64_t peak = 0;
   PG_TRY(pg_count_compute_histogram(c, 10000, in->segments != nullptr, in->histogram_path, &peak));

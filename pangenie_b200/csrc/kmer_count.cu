@@ -24,7 +24,7 @@
 
 namespace pg {
 
-constexpr int CT_THREADS = 512;                       // threads per counting CTA
+constexpr int CT_THREADS = 256;                       // threads per counting CTA
 constexpr int CT_TILE = CT_THREADS * 16;              // bytes loaded per tile (one uint4 per thread)
 constexpr int CT_HALO = 128;                          // look-ahead so k-mers may span tiles / chunks
 constexpr int CT_ADV = CT_TILE - CT_HALO;             // tile advance (multiple of 16)
@@ -226,7 +226,7 @@ __device__ __forceinline__ int block_exscan_max(int v, int* s_warp) {
 // table operations
 // ------------------------------------------------------------------------------------------------
 template <int OP>
-__device__ __forceinline__ bool resolve_slow(uint64_t kmer, uint64_t& slot, uint64_t* keys, uint64_t cap,
+__device__ __noinline__ bool resolve_slow(uint64_t kmer, uint64_t& slot, uint64_t* keys, uint64_t cap,
                                              unsigned long long* scalars, uint32_t& inserted) {
   // continues probing at `slot` (inclusive); returns true if the key is (now) present at `slot`
   for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
@@ -251,11 +251,27 @@ __device__ __forceinline__ bool resolve_slow(uint64_t kmer, uint64_t& slot, uint
 // ------------------------------------------------------------------------------------------------
 // pass 3: classify, compact, roll, probe
 // ------------------------------------------------------------------------------------------------
+// 4 bytes -> 4 symbols (0-3 base code, 4 = not a base), SIMD within a 32-bit word.
+__device__ __forceinline__ uint32_t codes4(uint32_t w) {
+  const uint32_t c = ((w >> 1) ^ (w >> 2)) & 0x03030303u;  // A/a=0 C/c=1 G/g=2 T/t=3
+  const uint32_t u = w & 0xDFDFDFDFu;                      // fold case
+  const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+  return (c & ok) | (0x04040404u & ~ok);
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], uint32_t i) {
+  const uint32_t x = i < 8 ? (i < 4 ? w[0] : w[1]) : (i < 12 ? w[2] : w[3]);
+  return (x >> (8 * (i & 3))) & 0xff;
+}
+
+// Code size matters here: the first version of this kernel was 12k SASS instructions and spent 67% of its
+// stall samples waiting for instruction fetch.  Loops are kept rolled, slow paths are not inlined.
 template <int OP>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, int is_fastq,
                   const uint32_t* __restrict__ tile_meta, uint32_t k, uint64_t* __restrict__ keys,
-                  uint32_t* __restrict__ counts, uint64_t cap, unsigned long long* __restrict__ scalars) {
+                  uint32_t* __restrict__ counts, uint64_t cap, uint32_t cap_q, uint32_t cap_sh,
+                  unsigned long long* __restrict__ scalars) {
   __shared__ __align__(16) uint8_t sym[CT_TILE + 2 * SYM_PAD];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
@@ -266,48 +282,54 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   const uint64_t pos0 = base + (uint64_t)tid * 16;
   const uint32_t meta = tile_meta[blockIdx.x];
 
-  // ---- 128-bit load of this thread's 16 bytes ('\0' beyond the end: classified as reset) ----
+  // ---- 128-bit load of this thread's 16 bytes; bytes past the end read as 0 and are never emitted ----
   uint32_t w[4] = {0, 0, 0, 0};
-  if (pos0 + 16 <= n_avail) {
+  const uint32_t nbytes = pos0 >= n_avail ? 0u : (uint32_t)min((uint64_t)16, n_avail - pos0);
+  if (nbytes == 16) {
     uint4 v = *reinterpret_cast<const uint4*>(text + pos0);
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  } else {
-    for (int i = 0; i < 16; ++i)
-      if (pos0 + i < n_avail) w[i >> 2] |= (uint32_t)(uint8_t)text[pos0 + i] << (8 * (i & 3));
-  }
-
-  // ---- line classification: symbols of my 16 bytes as nibbles (0-3 base, 4 reset) ----
-  uint64_t nib = 0;
-  uint32_t n_emit = 0, n_emit_owned = 0;
-  auto emit = [&](uint32_t s, uint64_t pos) {
-    nib |= (uint64_t)s << (4 * n_emit);
-    ++n_emit;
-    if (pos < owned_end) ++n_emit_owned;
-  };
-  if (is_fastq) {
-    uint32_t my_nl = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (pos0 + i < n_avail && ((w[i >> 2] >> (8 * (i & 3))) & 0xff) == '\n') ++my_nl;
-    uint32_t tot;
-    uint32_t line = (meta & 3u) + block_exscan_add(my_nl, s_warp, &tot);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const uint64_t pos = pos0 + i;
-      const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
-      if (pos >= n_avail) continue;  // past the end of the text: the trailing pad resets the window
-      if (b == '\n') {
-        if ((line & 3u) == 1u) emit(4u, pos);  // end of a sequence line: k-mers never span records
-        ++line;
-      } else if ((line & 3u) == 1u) {
-        emit(base_code(b), pos);
-      }
+  } else if (nbytes) {
+    // tail of the text: aligned words are still readable (buffers are padded / over-allocated by >= 16 B)
+#pragma unroll 1
+    for (uint32_t i = 0; i < nbytes; ++i) {
+      const uint32_t b = (uint32_t)(uint8_t)text[pos0 + i] << (8 * (i & 3));
+      if (i < 4) w[0] |= b; else if (i < 8) w[1] |= b; else if (i < 12) w[2] |= b; else w[3] |= b;
     }
-  } else {
-    int my_last = -1;
+  }
+  // newline map of my bytes (bit i set <=> byte i is '\n'), SIMD compare
+  uint32_t nlbits = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (pos0 + i < n_avail && ((w[i >> 2] >> (8 * (i & 3))) & 0xff) == '\n') my_last = tid * 16 + i;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t m = __vcmpeq4(w[i], 0x0a0a0a0au) & 0x01010101u;  // 0/1 per byte
+    nlbits |= (((m * 0x01020408u) >> 24) & 0xfu) << (4 * i);         // gather the 4 flags: byte j -> bit j
+  }
+  const uint32_t bytemask = nbytes >= 16 ? 0xffffu : ((1u << nbytes) - 1u);
+  nlbits &= bytemask;
+  const uint32_t owned_bytes = pos0 >= owned_end ? 0u : (uint32_t)min((uint64_t)16, owned_end - pos0);
+  const uint32_t ownedmask = owned_bytes >= 16 ? 0xffffu : ((1u << owned_bytes) - 1u);
+
+  // ---- which of my bytes are emitted as symbols (bit mask E); every emitted byte maps to codes4() ----
+  // FASTQ: byte i is emitted iff it lies in a sequence line (line index mod 4 == 1); the newline that ends the
+  // sequence line is emitted too and becomes a reset (code 4), so k-mers never span records.
+  // FASTA: sequence-line bytes except newlines are emitted; the newline ending a HEADER line emits the reset.
+  uint32_t E = 0, force_reset = 0;  // force_reset: emitted bytes whose symbol must be 4 regardless of codes4
+  if (is_fastq) {
+    uint32_t tot;
+    uint32_t line = (meta & 3u) + block_exscan_add(__popc(nlbits), s_warp, &tot);
+    uint32_t rest = nlbits, start = 0;
+#pragma unroll 1
+    while (true) {
+      const uint32_t p = rest ? (uint32_t)__ffs(rest) - 1u : 15u;  // segment [start, p] lies in line `line`
+      if ((line & 3u) == 1u) E |= (0xffffu >> (15u - p)) & ~((1u << start) - 1u);
+      if (!rest) break;
+      rest &= rest - 1u;
+      ++line;
+      start = p + 1u;
+      if (start > 15u) break;
+    }
+    E &= bytemask;
+  } else {
+    const int my_last = nlbits ? tid * 16 + (31 - __clz(nlbits)) : -1;
     const int last_before = block_exscan_max(my_last, s_warp_i);  // tile-relative index or -1
     uint32_t state;
     if (last_before >= 0) {
@@ -316,20 +338,24 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     } else {
       state = (meta >> 2) & 3u;
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const uint64_t pos = pos0 + i;
-      const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
-      if (pos >= n_avail) continue;
-      if (state == LS_LINE_START) state = b == '>' ? LS_HEADER : LS_SEQ;
-      if (b == '\n') {
-        if (state == LS_HEADER) emit(4u, pos);
-        state = LS_LINE_START;
-      } else if (state == LS_SEQ) {
-        emit(base_code(b), pos);
-      }
+    uint32_t rest = nlbits, start = 0;
+#pragma unroll 1
+    while (start < nbytes) {
+      if (state == LS_LINE_START) state = byte_of(w, start) == '>' ? LS_HEADER : LS_SEQ;
+      const uint32_t p = rest ? (uint32_t)__ffs(rest) - 1u : 16u;  // newline ending this line piece (16: none)
+      const uint32_t last = p < 16u ? p : 15u;
+      const uint32_t seg = (0xffffu >> (15u - last)) & ~((1u << start) - 1u);
+      if (state == LS_SEQ) E |= seg & ~(p < 16u ? (1u << p) : 0u);       // sequence bytes, newline dropped
+      else if (p < 16u) { E |= 1u << p; force_reset |= 1u << p; }        // header: only its newline, as a reset
+      if (p >= 16u) break;
+      rest &= rest - 1u;
+      state = LS_LINE_START;
+      start = p + 1u;
     }
+    E &= bytemask;
+    force_reset &= bytemask;
   }
+  const uint32_t n_emit = __popc(E), n_emit_owned = __popc(E & ownedmask);
 
   // ---- compaction into shared memory, shifted so every k-mer END lies at a compile-time offset ----
   uint32_t tot_packed;
@@ -337,7 +363,24 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   const uint32_t my_off = off_packed & 0xffffu;
   const uint32_t n_syms = tot_packed & 0xffffu, n_owned_syms = tot_packed >> 16;
   const uint32_t SHIFT = 33u - k;  // symbols are stored at sym[SHIFT + idx]; sym[0..SHIFT) = reset
-  for (uint32_t i = 0; i < n_emit; ++i) sym[SHIFT + my_off + i] = (uint8_t)((nib >> (4 * i)) & 0xf);
+  if (E) {
+    uint32_t sy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sy[i] = codes4(w[i]);
+    uint8_t* dst = sym + SHIFT + my_off;
+    if (E == 0xffffu && ((SHIFT + my_off) & 3u) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(dst)[i] = sy[i];
+    } else {
+      uint32_t rest = E;
+#pragma unroll 1
+      while (rest) {
+        const uint32_t i = (uint32_t)__ffs(rest) - 1u;
+        rest &= rest - 1u;
+        *dst++ = ((force_reset >> i) & 1u) ? (uint8_t)4 : (uint8_t)byte_of(sy, i);
+      }
+    }
+  }
   if ((uint32_t)tid < SHIFT) sym[tid] = 4;  // leading pad
   if (tid < 64) {                            // trailing pad: reads reach at most n_syms + 47
     const uint32_t p = SHIFT + n_syms + tid;
@@ -351,77 +394,78 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     uint32_t after = n_syms - n_owned_syms;
     if (after < k - 1) {
       bool open = true;
+#pragma unroll 1
       for (uint32_t i = 0; i < after; ++i)
         if (sym[SHIFT + n_owned_syms + i] > 3) open = false;
       if (open && n_owned_syms > 0 && sym[SHIFT + n_owned_syms - 1] < 4) atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_HALO);
     }
   }
 
-  // ---- rolling canonical k-mers: thread handles START indices [16 tid, 16 tid + 16) ----
+  // ---- rolling canonical k-mers + probes: thread handles START indices [16 tid, 16 tid + 16) ----
+  // Symbols [s0, s0+32) warm the window up, every later symbol ends one k-mer (start = end - 32 in shifted
+  // coordinates).  4 k-mers per iteration: 4 independent key loads are in flight before any is resolved.
   const uint32_t s0 = (uint32_t)tid * 16;
-  uint64_t can[16];
-  uint32_t valid = 0;
-  if (s0 < n_owned_syms) {
-    const uint4* sp = reinterpret_cast<const uint4*>(sym + s0);
-    uint4 q0 = sp[0], q1 = sp[1], q2 = sp[2];
-    uint32_t sw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+  const bool active = s0 < n_owned_syms;
+  uint32_t inserted = 0, nk = 0;
+  if (__any_sync(0xffffffffu, active)) {
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(sym + s0);
     const uint64_t mask = kmer_mask(k);
     const uint32_t rshift = 2 * (k - 1);
     uint64_t fwd = 0, rev = 0;
     uint32_t run = 0;
+#pragma unroll 1
+    for (int wd = 0; wd < 8; ++wd) {
+      const uint32_t xw = active ? sp[wd] : 0x04040404u;
 #pragma unroll
-    for (int p = 0; p < 48; ++p) {
-      const uint32_t c = (sw[p >> 2] >> (8 * (p & 3))) & 0xff;
-      if (c < 4) {
-        fwd = ((fwd << 2) | c) & mask;
-        rev = (rev >> 2) | ((uint64_t)(3 - c) << rshift);
-        ++run;
-      } else {
-        run = 0;
-      }
-      if (p >= 32) {  // end at shifted index s0+p  <=>  start index s0 + p - 32
-        const int j = p - 32;
-        can[j] = fwd < rev ? fwd : rev;
-        if (run >= k && s0 + j < n_owned_syms) valid |= 1u << j;
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t c = (xw >> (8 * b)) & 0xff;
+        fwd = ((fwd << 2) | (c & 3u)) & mask;
+        rev = (rev >> 2) | ((uint64_t)(3u - (c & 3u)) << rshift);
+        run = c < 4 ? run + 1 : 0;
       }
     }
-  } else {
+#pragma unroll 1
+    for (int wd = 8; wd < 12; ++wd) {
+      const uint32_t xw = active ? sp[wd] : 0x04040404u;
+      uint64_t cn[4], slot[4], key[4];
+      uint32_t vm = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) can[j] = 0;
-  }
-
-  // ---- probes: 4 independent key loads in flight per thread, then resolve ----
-  uint32_t inserted = 0;
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t c = (xw >> (8 * b)) & 0xff;
+        fwd = ((fwd << 2) | (c & 3u)) & mask;
+        rev = (rev >> 2) | ((uint64_t)(3u - (c & 3u)) << rshift);
+        run = c < 4 ? run + 1 : 0;
+        cn[b] = fwd < rev ? fwd : rev;
+        if (run >= k && s0 + (uint32_t)((wd - 8) * 4 + b) < n_owned_syms) vm |= 1u << b;
+      }
 #pragma unroll
-  for (int g = 0; g < 16; g += 4) {
-    uint64_t slot[4], key[4];
+      for (int i = 0; i < 4; ++i) {
+        slot[i] = home_slot(cn[i], cap_q, cap_sh);
+        key[i] = ((vm >> i) & 1u) ? keys[slot[i]] : 0;
+      }
+      nk += __popc(vm);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      slot[i] = __umul64hi(hash_kmer(can[g + i]), cap);
-      key[i] = ((valid >> (g + i)) & 1u) ? keys[slot[i]] : 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool v = (valid >> (g + i)) & 1u;
-      bool hit = false;
-      if (v) {
-        if (key[i] == can[g + i]) hit = true;
-        else if (OP == PG_OP_UPDATE && key[i] == EMPTY_KEY) hit = false;
-        else {
-          if (key[i] != EMPTY_KEY) slot[i] = slot[i] + 1 == cap ? 0 : slot[i] + 1;  // occupied by another key
-          hit = resolve_slow<OP>(can[g + i], slot[i], keys, cap, scalars, inserted);
+      for (int i = 0; i < 4; ++i) {
+        const bool v = (vm >> i) & 1u;
+        bool hit = false;
+        if (v) {
+          if (key[i] == cn[i]) hit = true;
+          else if (OP == PG_OP_UPDATE && key[i] == EMPTY_KEY) hit = false;
+          else {
+            if (key[i] != EMPTY_KEY) slot[i] = slot[i] + 1 == cap ? 0 : slot[i] + 1;  // occupied by another key
+            hit = resolve_slow<OP>(cn[i], slot[i], keys, cap, scalars, inserted);
+          }
         }
-      }
-      if (OP != PG_OP_PRIME) {
-        // warp-aggregated increment: lanes hitting the same slot elect one leader
-        const unsigned long long tag = hit ? (unsigned long long)slot[i] : (~0ull - (unsigned)(tid & 31));
-        const unsigned peers = __match_any_sync(0xffffffffu, tag);
-        if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(counts + slot[i], (uint32_t)__popc(peers));
+        if (OP != PG_OP_PRIME) {
+          // warp-aggregated increment: lanes hitting the same slot elect one leader
+          const unsigned long long tag = hit ? (unsigned long long)slot[i] : (~0ull - (unsigned)(tid & 31));
+          const unsigned peers = __match_any_sync(0xffffffffu, tag);
+          if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(counts + slot[i], (uint32_t)__popc(peers));
+        }
       }
     }
   }
   // statistics: distinct keys inserted, k-mers processed
-  uint32_t nk = __popc(valid);
   for (int o = 16; o > 0; o >>= 1) {
     inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
     nk += __shfl_xor_sync(0xffffffffu, nk, o);
@@ -436,10 +480,10 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 // lookups, histogram, sums
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, const uint64_t* __restrict__ keys,
-                                                 const uint32_t* __restrict__ counts, uint64_t cap) {
+                                                 const uint32_t* __restrict__ counts, uint64_t cap, uint32_t q, uint32_t sh) {
   const uint64_t rc = revcomp_2bit(code, k);
   const uint64_t can = code < rc ? code : rc;
-  uint64_t slot = __umul64hi(hash_kmer(can), cap);
+  uint64_t slot = home_slot(can, q, sh);
   for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
     const uint64_t cur = keys[slot];
     if (cur == can) return counts[slot];
@@ -451,9 +495,9 @@ __device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, cons
 
 __global__ void lookup_kernel(const uint64_t* __restrict__ codes, uint64_t n, uint32_t k,
                               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t cap,
-                              uint64_t* __restrict__ out) {
+                              uint32_t q, uint32_t sh, uint64_t* __restrict__ out) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    out[i] = table_lookup(codes[i], k, keys, counts, cap);
+    out[i] = table_lookup(codes[i], k, keys, counts, cap, q, sh);
   }
 }
 
@@ -534,13 +578,13 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
   tile_scan_kernel<<<1, 1024, 0, c->stream>>>(d_text, n, n_tiles, nlc, lnl, is_fastq, meta, c->d_scalars);
   switch (op) {
     case PG_OP_COUNT:
-      count_tile_kernel<PG_OP_COUNT><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->d_scalars);
+      count_tile_kernel<PG_OP_COUNT><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
       break;
     case PG_OP_PRIME:
-      count_tile_kernel<PG_OP_PRIME><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->d_scalars);
+      count_tile_kernel<PG_OP_PRIME><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
       break;
     default:
-      count_tile_kernel<PG_OP_UPDATE><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->d_scalars);
+      count_tile_kernel<PG_OP_UPDATE><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
   }
   count_launch(3);
   PG_CUDA(cudaGetLastError());
@@ -658,8 +702,16 @@ extern "C" pg_counter* pg_count_new(uint32_t k, uint64_t max_distinct, int devic
   c->device = device;
   c->k = k;
   c->max_distinct = std::max<uint64_t>(max_distinct, 1024);
-  c->capacity = (uint64_t)((double)c->max_distinct / 0.6) + 1024;
-  c->capacity = (c->capacity + 3) & ~3ull;
+  {
+    uint64_t want = (uint64_t)((double)c->max_distinct / 0.6) + 1024;
+    uint32_t sh = 0;
+    while ((want >> sh) >= (1ull << 31)) ++sh;  // keep q below 2^31
+    if (sh < 2) sh = 2;                          // capacity multiple of 4 (vectorised scans of counts[])
+    const uint64_t q = (want + (1ull << sh) - 1) >> sh;
+    c->cap_q = (uint32_t)q;
+    c->cap_sh = sh;
+    c->capacity = q << sh;
+  }
   auto bail = [&](const char* what, cudaError_t e) {
     fail(PG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     pg_count_destroy(c);
@@ -778,7 +830,7 @@ static int lookup_codes(const pg_counter* c, const uint64_t* h_codes, uint64_t n
   cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
   cudaMemcpyAsync(d_codes, h_codes, n * 8, cudaMemcpyHostToDevice, s);
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-  lookup_kernel<<<grid, 256, 0, s>>>(d_codes, n, c->k, c->keys, c->counts, c->capacity, d_out);
+  lookup_kernel<<<grid, 256, 0, s>>>(d_codes, n, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, d_out);
   count_launch();
   cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, s);
   e = cudaStreamSynchronize(s);

@@ -23,6 +23,9 @@ ncu)
 ncu_h64)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"skeleton_kernel|block_kernel" -s 3 -c 2 -o $out/prof_h64_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload h64s > $out/ncu_h64_$tag.out 2>&1; tail -3 $out/ncu_h64_$tag.out;;
+ncu_count)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"count_tile_kernel" -s 3 -c 2 -o $out/prof_count_$tag \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/ncu_count_$tag.out 2>&1; tail -3 $out/ncu_count_$tag.out;;
 sanitizer)
   timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_hmm.py tests/test_gpu_counting.py -m gpu -q -p no:cacheprovider \
      -k "reference_vector or edge_cases or options or kmercounter_vectors" 2>&1 | tail -60 > $out/sanitizer_$tag.log; tail -8 $out/sanitizer_$tag.log;;
