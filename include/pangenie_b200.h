@@ -260,6 +260,11 @@ int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_t reads_len
                            uint64_t segments_len, uint32_t k, uint64_t hash_size, double regularization,
                            const pg_hmm_params* params, uint64_t* kmer_abundance_peak);
 int pg_engine_fetch(pg_engine* e, uint32_t n_chrom, pg_panel* panels, pg_hmm_result* results);
+/** Everything after counting (histogram peak -> ProbabilityTable -> fill -> emission + forward-backward) on the
+ *  loaded panels, against a counter the caller filled — e.g. one whose count array was all-reduced over the GPUs
+ *  that each counted a shard of the reads.  `largest_peak` as in computeHistogram. */
+int pg_engine_run_counted(pg_engine* e, const pg_counter* c, int largest_peak, double regularization,
+                          const pg_hmm_params* params, uint64_t* kmer_abundance_peak);
 
 /** Empties a counter (all keys removed, counts zero) so its HBM allocation can be reused. */
 int pg_count_clear(pg_counter* c);

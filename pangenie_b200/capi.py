@@ -112,7 +112,7 @@ EXPORTS = [
     "pg_result_layout", "pg_engine_create", "pg_engine_destroy", "pg_hmm_run", "pg_emission_run",
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
     "pg_count_device_arrays", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
-    "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch",
+    "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted",
 ]
 
 
@@ -176,6 +176,7 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "engine_load", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgHmmResult)])
         _sig(lib, p + "engine_run_resident", i32, [vp, vp, u64, vp, u64, u32, u64, dbl, C.POINTER(PgHmmParams), C.POINTER(u64)])
         _sig(lib, p + "engine_fetch", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgHmmResult)])
+        _sig(lib, p + "engine_run_counted", i32, [vp, vp, i32, dbl, C.POINTER(PgHmmParams), C.POINTER(u64)])
         _sig(lib, p + "genotype_run", i32, [vp, C.POINTER(PgGenotypeInput), u32, C.POINTER(PgPanel), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult), C.POINTER(u64)])
     else:
         # oracles: same data arguments, no engine handle

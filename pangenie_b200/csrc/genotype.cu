@@ -1077,6 +1077,37 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   return PG_OK;
 }
 
+// histogram peak -> ProbabilityTable -> fill -> emission + forward-backward on the loaded panels
+static int engine_after_count(pg_engine* e, const pg_counter* c, bool largest_peak, double regularization,
+                              const pg_hmm_params* params, uint64_t* kmer_abundance_peak) {
+  uint64_t peak = 0;
+  cudaEvent_t h0, h1;
+  cudaEventCreate(&h0);
+  cudaEventCreate(&h1);
+  cudaEventRecord(h0, c->stream);
+  int st = pg_count_compute_histogram(c, 10000, largest_peak, nullptr, &peak);
+  cudaEventRecord(h1, c->stream);
+  cudaEventSynchronize(h1);
+  float hms = 0;
+  cudaEventElapsedTime(&hms, h0, h1);
+  cudaEventDestroy(h0);
+  cudaEventDestroy(h1);
+  if (st != PG_OK) return st;
+  if (kmer_abundance_peak) *kmer_abundance_peak = peak;
+  pg_probtable table;
+  PG_TRY(pg_probtable_init(&table, (uint16_t)(peak / 4), (uint16_t)(peak * 4), (uint16_t)(2 * peak), regularization));
+  struct TGuard {
+    pg_probtable* t;
+    ~TGuard() { pg_probtable_free(t); }
+  } tguard{&table};
+  PG_TRY(engine_fill(e, c, peak));
+  const double fill_ms = e->tm.fill_ms;
+  PG_TRY(engine_hmm(e, &table, params));
+  e->tm.fill_ms = fill_ms;
+  e->tm.histogram_ms = hms;
+  return PG_OK;
+}
+
 extern "C" int pg_engine_load(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_hmm_result* layouts) {
   clear_error();
   if (!e || !panels || !layouts) return fail(PG_ERR_ARG, "null argument");
@@ -1113,31 +1144,21 @@ extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_
   e->tm.count_ms = c->last_feed_ms;
   e->tm.kmers_counted = c->kmers_seen;
   e->tm.text_bytes = reads_len;
-  uint64_t peak = 0;
-  cudaEvent_t h0, h1;
-  cudaEventCreate(&h0);
-  cudaEventCreate(&h1);
-  cudaEventRecord(h0, c->stream);
-  int st = pg_count_compute_histogram(c, 10000, d_segments != nullptr, nullptr, &peak);
-  cudaEventRecord(h1, c->stream);
-  cudaEventSynchronize(h1);
-  float hms = 0;
-  cudaEventElapsedTime(&hms, h0, h1);
-  cudaEventDestroy(h0);
-  cudaEventDestroy(h1);
-  if (st != PG_OK) return st;
-  if (kmer_abundance_peak) *kmer_abundance_peak = peak;
-  pg_probtable table;
-  PG_TRY(pg_probtable_init(&table, (uint16_t)(peak / 4), (uint16_t)(peak * 4), (uint16_t)(2 * peak), regularization));
-  struct TGuard {
-    pg_probtable* t;
-    ~TGuard() { pg_probtable_free(t); }
-  } tguard{&table};
-  PG_TRY(engine_fill(e, c, peak));
-  const double fill_ms = e->tm.fill_ms;
-  PG_TRY(engine_hmm(e, &table, params));
-  e->tm.fill_ms = fill_ms;
-  e->tm.histogram_ms = hms;
+  PG_TRY(engine_after_count(e, c, d_segments != nullptr, regularization, params, kmer_abundance_peak));
+  e->tm.kernel_launches = g_launches - l0;
+  return PG_OK;
+}
+
+extern "C" int pg_engine_run_counted(pg_engine* e, const pg_counter* c, int largest_peak, double regularization,
+                                     const pg_hmm_params* params, uint64_t* kmer_abundance_peak) {
+  clear_error();
+  if (!e || !c || !params) return fail(PG_ERR_ARG, "null argument");
+  if (!e->has_codes) return fail(PG_ERR_ARG, "call pg_engine_load first");
+  const uint64_t l0 = g_launches;
+  const pg_timings keep = e->tm;
+  PG_TRY(engine_after_count(e, c, largest_peak != 0, regularization, params, kmer_abundance_peak));
+  e->tm.count_ms = keep.count_ms;
+  e->tm.prime_ms = keep.prime_ms;
   e->tm.kernel_launches = g_launches - l0;
   return PG_OK;
 }

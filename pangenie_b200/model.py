@@ -131,6 +131,9 @@ class KmerCounter:
                                                                  filename.encode() if filename else None, C.byref(out)))
         return out.value
 
+    def clear(self):
+        _check(self._lib, self._lib.pg_count_clear(self._h))
+
     def distinct(self) -> int:
         return int(self._lib.pg_count_distinct(self._h))
 
@@ -259,6 +262,13 @@ class Engine:
         sa, sl, _k2 = _bytes_arg(d_segments)
         peak = C.c_uint64(0)
         _check(self._lib, self._lib.pg_engine_run_resident(self._h, ra_, rl, sa, sl, k, hash_size, regularization, C.byref(prm), C.byref(peak)))
+        return peak.value
+
+    def run_counted(self, counter: "KmerCounter", largest_peak: bool = True, regularization=0.01, **kw) -> int:
+        """Histogram peak -> table -> fill -> HMM on the loaded panels against an externally filled counter."""
+        prm, _keep = hmm_params(**kw)
+        peak = C.c_uint64(0)
+        _check(self._lib, self._lib.pg_engine_run_counted(self._h, counter.handle, int(largest_peak), regularization, C.byref(prm), C.byref(peak)))
         return peak.value
 
     def fetch(self):
