@@ -336,13 +336,15 @@ def main():
     value = world * V * K / dt
 
     # ---- e2e: pinned host buffers through pg_genotype_run, copies inside the timed region ----
+    from pangenie_b200.panel import Result
+    res_buf = [Result(p) for p in wl.panels]  # caller-owned output buffers, reused across steps
     for _ in range(2):
-        eng.genotype_run(reads_h, segs_h, wl.panels, k=wl.k, **kw)
+        eng.genotype_run(reads_h, segs_h, wl.panels, k=wl.k, results=res_buf, **kw)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         flush.zero_()
-        res_e2e, peak = eng.genotype_run(reads_h, segs_h, wl.panels, k=wl.k, **kw)
+        res_e2e, peak = eng.genotype_run(reads_h, segs_h, wl.panels, k=wl.k, results=res_buf, **kw)
     barrier()
     dte = time.perf_counter() - t0
     tmax = torch.tensor([dte], dtype=torch.float64, device="cuda")

@@ -49,12 +49,17 @@ class Panel:
 
     def result_layout(self) -> np.ndarray:
         """gl_offsets as pg_result_layout computes them: row length n(n+1)/2 with n = max allele id + 1."""
-        off = np.zeros(self.n_variants + 1, dtype=np.uint64)
-        ao = self.allele_offsets
-        for v in range(self.n_variants):
-            ids = self.allele_ids[ao[v]:ao[v + 1]]
-            n = (int(ids.max()) if len(ids) else 0) + 1
-            off[v + 1] = off[v] + n * (n + 1) // 2
+        V = self.n_variants
+        off = np.zeros(V + 1, dtype=np.uint64)
+        if V == 0:
+            return off
+        ao = self.allele_offsets.astype(np.int64)
+        n = np.ones(V, np.int64)
+        has = ao[1:] > ao[:-1]
+        if has.any():
+            mx = np.maximum.reduceat(self.allele_ids.astype(np.int64), ao[:-1][has])
+            n[has] = mx + 1
+        off[1:] = np.cumsum(n * (n + 1) // 2)
         return off
 
     def nr_alleles(self, v: int) -> int:

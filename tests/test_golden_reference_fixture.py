@@ -1,0 +1,72 @@
+"""Golden fixture of the reference at the jellyfish boundary (reference tests/CommandsTest.cpp:17-95):
+inputs  tests/data/index_path_segments.fasta (PRIME), region-reads.fa (FASTQ, UPDATE), index_chr1_kmers.tsv.gz
+expect  kmer_abundance_peak == 18 (CommandsTest.cpp:57) and the per-variant counts / local coverages stored in
+        tests/data/region_UniqueKmersList.cereal — produced by the real PanGenie with libjellyfish.
+The files under tests/golden/counting/ are byte copies of those reference test-data files (data, not source);
+pangenie_b200/refindex.py decodes them."""
+import os
+
+import numpy as np
+import pytest
+
+import pangenie_b200 as pg
+from pangenie_b200 import refindex
+from tests import oracles
+from tests.helpers import assert_results_close
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "counting")
+
+
+def _load():
+    k, panels, _ = refindex.read_unique_kmers_map(os.path.join(G, "index_UniqueKmersMap.cereal"))
+    panel = refindex.attach_kmers_tsv(panels["chr1"], os.path.join(G, "index_chr1_kmers.tsv.gz"))
+    _, filled, _ = refindex.read_unique_kmers_map(os.path.join(G, "region_UniqueKmersList.cereal"))
+    reads = np.fromfile(os.path.join(G, "region-reads.fa"), np.uint8)
+    segs = np.fromfile(os.path.join(G, "index_path_segments.fasta"), np.uint8)
+    return k, panel, filled["chr1"], reads, segs
+
+
+def test_archive_decoding():
+    k, panel, want, reads, segs = _load()
+    assert k == 31 and panel.n_variants == 2 and panel.n_paths == 215
+    assert reads[0] == ord("@") and segs[0] == ord(">")
+    assert np.array_equal(panel.allele_ids, want.allele_ids) and np.array_equal(panel.allele_kmer_mask, want.allele_kmer_mask)
+    assert np.array_equal(panel.path_to_allele, want.path_to_allele)
+
+
+def test_counting_restatement_reproduces_jellyfish_counts(oracle):
+    k, panel, want, reads, segs = _load()
+    o = oracles.OracleCounter(oracle, reads, segs, k)
+    # The reference test hard-codes kmer_abundance_peak = 18 (CommandsTest.cpp:57) for the HMM it compares with.
+    # The 313-bp region yields a histogram of ~370 keys with three near-equal local maxima; the reference's own
+    # Histogram code applied to the restated counts picks 35, so the peak itself is NOT pinned by this fixture
+    # (it is decided by a handful of graph k-mers outside the 154 pinned ones) — the counts and coverages are.
+    assert o.computeHistogram(10000, True) in (18, 35)
+    o.fill_counts(18, [panel])
+    assert np.array_equal(panel.kmer_counts, want.kmer_counts)
+    assert np.array_equal(panel.coverage, want.coverage)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_jellyfish_counts_and_reference_hmm(engine, oracle):
+    k, panel, want, reads, segs = _load()
+    g = pg.KmerCounter(reads, segs, k, hash_size=100000)
+    o = oracles.OracleCounter(oracle, reads, segs, k)
+    assert np.array_equal(g.histogram(), o.histogram()) and g.computeHistogram(10000, True) == o.computeHistogram(10000, True)
+    engine.fill_counts(g, 18, [panel])   # peak as hard-coded by the reference test (CommandsTest.cpp:57)
+    assert np.array_equal(panel.kmer_counts, want.kmer_counts) and np.array_equal(panel.coverage, want.coverage)
+    res = engine.hmm_run([panel], pg.ProbabilityTable(18 // 4, 18 * 4, 2 * 18, 0.01), recombrate=1.26, effective_N=0.00001)
+    # P = 215 paths, up to 45 alleles per variant: the reference's HMM on the same filled panel
+    table = pg.ProbabilityTable(18 // 4, 18 * 4, 2 * 18, 0.01)
+    ref = oracles.load_ref()
+    lib, pre = (ref, "pgr_") if ref is not None else (oracle, "pgo_")
+    exp = oracles.cpu_hmm_run(lib, pre, [want], table, recombrate=1.26, effective_N=0.00001)[0]
+    assert_results_close(res[0], exp, label="CommandsTest fixture")
+
+
+def test_oracle_hmm_on_fixture_matches_reference(oracle, ref):
+    k, panel, want, reads, segs = _load()
+    table = pg.ProbabilityTable(18 // 4, 18 * 4, 2 * 18, 0.01)
+    a = oracles.cpu_hmm_run(oracle, "pgo_", [want], table, recombrate=1.26, effective_N=0.00001)[0]
+    b = oracles.cpu_hmm_run(ref, "pgr_", [want], table, recombrate=1.26, effective_N=0.00001)[0]
+    assert_results_close(a, b, rtol=1e-12, label="fixture")
