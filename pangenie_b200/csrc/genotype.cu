@@ -5,6 +5,7 @@
 // (src/graph.cpp:206-240).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -443,18 +444,28 @@ static bool pick_cfg(uint32_t P, TileCfg& c) {
   return false;
 }
 
+// PG_BLOCK_MINB=1 selects the un-capped-register variant of the (4,17,1) block kernel (tuning knob)
+static bool minb1() {
+  static const bool v = [] { const char* e = getenv("PG_BLOCK_MINB"); return e && e[0] == '1'; }();
+  return v;
+}
+
 template <int L, int CPL, int RPW, int NT>
 static cudaError_t launch_pair(const ChainParams& p, uint32_t n_chrom, int grid_blocks, cudaStream_t s, bool skeleton, bool blocks) {
   const size_t smem = sizeof(ChainSmem);
   if (skeleton) skeleton_kernel<L, CPL, RPW, NT><<<dim3(n_chrom, 2), NT, smem, s>>>(p);
-  if (blocks) block_kernel<L, CPL, RPW, NT><<<grid_blocks, NT, smem, s>>>(p);
+  if (blocks) {
+    if (NT == 288 && minb1()) block_kernel<L, CPL, RPW, NT, 1><<<grid_blocks, NT, smem, s>>>(p);
+    else block_kernel<L, CPL, RPW, NT><<<grid_blocks, NT, smem, s>>>(p);
+  }
   return cudaGetLastError();
 }
 
 template <int L, int CPL, int RPW, int NT>
 static int occupancy_of() {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT>, NT, sizeof(ChainSmem));
+  if (NT == 288 && minb1()) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, 1>, NT, sizeof(ChainSmem));
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT>, NT, sizeof(ChainSmem));
   return n;
 }
 

@@ -205,6 +205,19 @@ struct Chain {
       for (int s = 0; s < CPL; ++s) x[r][s] = (rok && ((vmask >> s) & 1u)) ? src[(size_t)(r * CPL + s) * NT + threadIdx.x] : 0.0;
     }
   }
+  // stored forward column -> registers (issued early so the latency overlaps the reductions of the step)
+  __device__ __forceinline__ void load_cells(const double* src, bool dead_uniform, double (&u)[RPW][CPL]) const {
+    const double uni = 1.0 / ((double)P * (double)P);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const bool rok = row(r) < P;
+#pragma unroll
+      for (int s = 0; s < CPL; ++s) {
+        const bool ok = rok && ((vmask >> s) & 1u);
+        u[r][s] = ok ? (dead_uniform ? uni : src[(size_t)(r * CPL + s) * NT + threadIdx.x]) : 0.0;
+      }
+    }
+  }
   // publish the row sums of x into rs[buf]; caller must sync() before anyone reads them
   __device__ __forceinline__ void publish_rowsums(int buf) {
 #pragma unroll
@@ -235,7 +248,7 @@ struct Chain {
   // ---- one column.  FIRST: no transition (pre = 1).  WITH_POST: accumulate F o pre (u = stored F_t). ----
   // Reads rs[cbuf] (row sums of x), writes rs[nbuf]; coefficients (t-1 -> t) forward, (t -> t+1) backward.
   template <bool BACKWARD, bool FIRST, bool WITH_POST>
-  __device__ __forceinline__ void step(int slot, int cbuf, int nbuf, double Tprev, const double* ucol, bool u_dead, int wbuf) {
+  __device__ __forceinline__ void step(int slot, int cbuf, int nbuf, double Tprev, const double (&u)[RPW][CPL], int wbuf) {
     const double* d = desc_d(slot);
     const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
     const double S = (double)P * (double)P;
@@ -252,12 +265,9 @@ struct Chain {
         cc = BACKWARD ? 1.0 / S : d[o + 3] / S;
       }
     }
-    const double uni = 1.0 / S;
     // the reference's backward cells of a dead column are all zero (hmm.cpp:348-352 with zero helpers)
     const double wscale = dead ? 0.0 : 1.0;
-    double rj[CPL];  // row sums of my columns (rs is zero-padded beyond P)
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) rj[s] = FIRST ? 0.0 : sm->rs[cbuf][col0 + s];
+    const double* rj = &sm->rs[cbuf][col0];  // row sums of my columns (rs is zero-padded beyond P)
 
     if (A <= 2) {
       // ------------- biallelic column: allele indices come as bitmasks, emission by select -------------
@@ -278,10 +288,7 @@ struct Chain {
           const bool c1 = (jb >> s) & 1u;
           const double pre = FIRST ? 1.0 : fma(ca, x[r][s], fma(cb, rj[s], rho));
           if (WITH_POST) {
-            double uu = 0.0;
-            if (ok && rok) uu = ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
-            if (u_dead) uu = (ok && rok) ? uni : 0.0;
-            const double wv = uu * pre * wscale;
+            const double wv = u[r][s] * pre * wscale;
             w0 += c1 ? 0.0 : wv;  // accumulated separately: total - w1 would cancel
             w1 += c1 ? wv : 0.0;
           }
@@ -331,9 +338,7 @@ struct Chain {
         const uint32_t aj = ok ? aidx[col0 + s] : 0;
         const double pre = FIRST ? 1.0 : fma(ca, x[r][s], fma(cb, rj[s], rho));
         if (WITH_POST) {
-          double uu = 0.0;
-          if (ok) uu = u_dead ? uni : ucol[(size_t)(r * CPL + s) * NT + threadIdx.x];
-          const double wv = uu * pre * wscale;
+          const double wv = u[r][s] * pre * wscale;
           if (fastA) {
 #pragma unroll
             for (int q = 0; q < HMM_FAST_A; ++q) wc[q] += (aj == (uint32_t)q) ? wv : 0.0;
@@ -396,6 +401,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
   ch.sync();
   const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
   const size_t PP = p.state_stride;
+  double nou[RPW][CPL];  // unused (no posterior in the skeleton); the compiler drops it
   constexpr int D = HMM_PREFETCH;
   int cur = 0;
   if (blockIdx.y == 0) {
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
     }
     cp_async_wait<D - 1>();
     ch.sync();
-    ch.template step<false, true, false>(slot, 0, 0, 0.0, nullptr, false, 0);
+    ch.template step<false, true, false>(slot, 0, 0, 0.0, nou, 0);
     ch.prefetch_desc(c0 + D, c0, c1, pslot);
     pslot = ch.slot_next(pslot);
     cp_async_wait<D - 1>();
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
       }
       --until_ckpt;
       const double T = ch.total(cur);
-      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nou, 0);
       ch.prefetch_desc(t + D, c0, c1, pslot);
       pslot = ch.slot_next(pslot);
       cp_async_wait<D - 1>();
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
     }
     cp_async_wait<D - 1>();
     ch.sync();
-    ch.template step<true, true, false>(slot, 0, 0, 0.0, nullptr, false, 0);
+    ch.template step<true, true, false>(slot, 0, 0, 0.0, nou, 0);
     int rel = (c1 - 1 - c0) % B;        // position of column t inside its block (one division per chain)
     uint32_t blk = cc.blk_begin + (uint32_t)((c1 - 1 - c0) / B);
     if (rel == 0) ch.store_state(p.ckpt_bwd + (size_t)(blk - 1) * PP);
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
       }
       --rel;
       const double T = ch.total(cur);
-      ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nou, 0);
       if (rel == 0) ch.store_state(p.ckpt_bwd + (size_t)(blk - 1) * PP);
       ch.prefetch_desc(t - D, c0, c1, pslot);
       pslot = slot_prev(pslot);
@@ -477,8 +483,8 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
 // -------------------------------------------------------------------------------------------------
 // phase 2: block forward-backward with fused posterior.  Persistent CTAs pull (chromosome, block) jobs.
 // -------------------------------------------------------------------------------------------------
-template <int L, int CPL, int RPW, int NT>
-__global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const ChainParams p) {
+template <int L, int CPL, int RPW, int NT, int MINB = (NT <= 288 ? 2 : 1)>
+__global__ void __launch_bounds__(NT, MINB) block_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
   __shared__ uint32_t s_job;
@@ -489,6 +495,7 @@ __global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const Ch
   double* buf = p.block_buf + (size_t)blockIdx.x * p.B * PP;
   constexpr int D = HMM_PREFETCH;
   constexpr int NW = NT / 32;
+  double nou[RPW][CPL], ureg[RPW][CPL];
   auto slot_prev = [](int s) { return (s - 1) & (HMM_NSLOT - 1); };
   while (true) {
     ch.sync();
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const Ch
     if (jb.y == 0) {
       cp_async_wait<D - 1>();
       ch.sync();
-      ch.template step<false, true, false>(slot, 0, 0, 0.0, nullptr, false, 0);
+      ch.template step<false, true, false>(slot, 0, 0, 0.0, nou, 0);
       ch.store_state(bcol);
       bcol += PP;
       ch.prefetch_desc(cb + D, cb, ce, pslot);
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const Ch
     for (; t < ce; ++t) {
       const double T = ch.total(cur);
       if (threadIdx.x == 0 && t > cb) sm->tf[t - 1 - cb] = T;
-      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nullptr, false, 0);
+      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nou, 0);
       ch.store_state(bcol);
       bcol += PP;
       ch.prefetch_desc(t + D, cb, ce, pslot);
@@ -566,7 +573,8 @@ __global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const Ch
     if (ce == c1) {
       cp_async_wait<D - 1>();
       ch.sync();
-      ch.template step<true, true, true>(slot, 0, 0, 0.0, bcol, !(sm->tf[t - cb] > 0.0), wbuf);
+      ch.load_cells(bcol, !(sm->tf[t - cb] > 0.0), ureg);
+      ch.template step<true, true, true>(slot, 0, 0, 0.0, ureg, wbuf);
       bcol -= PP;
       ch.prefetch_desc(t - D, cb, ce, pslot);
       pslot = slot_prev(pslot);
@@ -584,6 +592,7 @@ __global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const Ch
       ch.sync();
     }
     for (; t >= cb; --t) {
+      ch.load_cells(bcol, !(sm->tf[t - cb] > 0.0), ureg);  // issued first: overlaps the writer and the reductions
       if (pending_slot >= 0 && ch.w == pending_w) ch.write_posterior(pending_slot, pending_wbuf);
       const double T = ch.total(cur);
       if (threadIdx.x == 0 && t + 1 < c1) p.tot_bwd[t + 1] = T;
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(NT, (NT <= 288 ? 2 : 1)) block_kernel(const Ch
         const char* nxt = reinterpret_cast<const char*>(bcol - 2 * PP);
         for (size_t o = (size_t)threadIdx.x * 128; o < PP * 8; o += (size_t)NT * 128) prefetch_l2(nxt + o);
       }
-      ch.template step<true, false, true>(slot, cur, cur ^ 1, T, bcol, !(sm->tf[t - cb] > 0.0), wbuf);
+      ch.template step<true, false, true>(slot, cur, cur ^ 1, T, ureg, wbuf);
       bcol -= PP;
       ch.prefetch_desc(t - D, cb, ce, pslot);
       pslot = slot_prev(pslot);

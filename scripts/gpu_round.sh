@@ -20,6 +20,8 @@ launches)
 ncu)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"block_kernel|count_tile_kernel" -s 4 -c 4 -o $out/prof_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/ncu_$tag.out 2>&1; tail -3 $out/ncu_$tag.out;;
+bench_h64_minb)
+  PG_BLOCK_MINB=1 timeout 1200 python bench.py --steps 3 --warmup 3 --workload h64s --no-cpu-baseline > $out/bench_h64s_minb1_$tag.json 2> $out/bench_h64s_minb1_$tag.err; tail -c 1200 $out/bench_h64s_minb1_$tag.json | head -c 1200; tail -3 $out/bench_h64s_minb1_$tag.err;;
 ncu_h64)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"skeleton_kernel|block_kernel" -s 3 -c 2 -o $out/prof_h64_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload h64s > $out/ncu_h64_$tag.out 2>&1; tail -3 $out/ncu_h64_$tag.out;;
