@@ -103,10 +103,14 @@ int pg_count_histogram(const pg_counter* c, uint64_t max_count, uint64_t* bins);
 int pg_count_compute_histogram(const pg_counter* c, uint64_t max_count, int largest_peak,
                                const char* filename, uint64_t* kmer_abundance_peak);
 
-/** Device views for the one cross-GPU exchange: `keys` (u64[capacity]) and `counts`
- *  (u32[capacity]) DEVICE addresses, so a host framework (torch.distributed / NCCL) can broadcast the primed
- *  key array and all-reduce the count array of layout-identical tables. */
-int pg_count_device_arrays(const pg_counter* c, uint64_t* keys_addr, uint64_t* counts_addr, uint64_t* capacity);
+/** Device views for the cross-GPU exchange.  `slots_addr`: the table itself, capacity/4 buckets of 64 bytes
+ *  (4 u64 keys, 4 u32 counts, 16 B padding; 16 bytes per slot) — broadcast it (as bytes) after PRIME so every GPU holds
+ *  a layout-identical table.
+ *  `counts_addr`: a contiguous u32[capacity] staging array; pg_count_export_counts copies the counts into it,
+ *  the host framework all-reduces it (torch.distributed / NCCL), pg_count_import_counts writes the sums back. */
+int pg_count_device_arrays(const pg_counter* c, uint64_t* slots_addr, uint64_t* counts_addr, uint64_t* capacity);
+int pg_count_export_counts(pg_counter* c);
+int pg_count_import_counts(pg_counter* c);
 /** k-mers processed / device milliseconds of the last pg_count_feed* call (measurement hooks). */
 uint64_t pg_count_kmers_seen(const pg_counter* c);
 double pg_count_last_ms(const pg_counter* c);

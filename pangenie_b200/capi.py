@@ -111,7 +111,7 @@ EXPORTS = [
     "pg_probtable_init", "pg_probtable_modify", "pg_probtable_get", "pg_probtable_free",
     "pg_result_layout", "pg_engine_create", "pg_engine_destroy", "pg_hmm_run", "pg_emission_run",
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
-    "pg_count_device_arrays", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
+    "pg_count_device_arrays", "pg_count_export_counts", "pg_count_import_counts", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
     "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted",
 ]
 
@@ -143,6 +143,8 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
             _sig(lib, p + "count_feed_device", i32, [vp, vp, u64, i32])
             _sig(lib, p + "count_capacity", u64, [vp])
             _sig(lib, p + "count_device_arrays", i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)])
+            _sig(lib, p + "count_export_counts", i32, [vp])
+            _sig(lib, p + "count_import_counts", i32, [vp])
             _sig(lib, p + "count_kmers_seen", u64, [vp])
             _sig(lib, p + "count_last_ms", dbl, [vp])
             _sig(lib, p + "count_clear", i32, [vp])

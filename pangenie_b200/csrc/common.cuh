@@ -100,6 +100,39 @@ __device__ __forceinline__ uint64_t home_slot(uint64_t kmer, uint32_t q, uint32_
 
 constexpr uint64_t EMPTY_KEY = ~0ULL;  // never a canonical k-mer for k <= 32 (all-T canonicalises to all-A)
 
+// The table is an array of 64-byte buckets = one DRAM burst: 4 keys (32 B, two 128-bit loads), their 4 counts
+// (16 B) and 16 B of padding.  A key lives in the first free position of its home bucket, else of the next bucket
+// (bucket-linear probing); positions fill left to right and nothing is ever deleted, so an EMPTY position ends a
+// search.  "slot" s denotes position s & 3 of bucket s >> 2.
+struct __align__(64) KmerBucket {
+  unsigned long long key[4];
+  uint32_t cnt[4];
+  uint32_t pad[4];
+};
+
+/** canonicalise + look up; 0 if absent (getKmerAbundance, reference src/jellyfishcounter.cpp:87-104) */
+__device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, const KmerBucket* __restrict__ tab, uint64_t cap,
+                                                 uint32_t q, uint32_t sh) {
+  const uint64_t rc = revcomp_2bit(code, k);
+  const uint64_t can = code < rc ? code : rc;
+  uint64_t b = home_slot(can, q, sh) >> 2;
+  const uint64_t nb = cap >> 2;
+  for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
+    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&tab[b].key[0]);
+    const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&tab[b].key[2]);
+    if (k01.x == can) return tab[b].cnt[0];
+    if (k01.x == EMPTY_KEY) return 0;
+    if (k01.y == can) return tab[b].cnt[1];
+    if (k01.y == EMPTY_KEY) return 0;
+    if (k23.x == can) return tab[b].cnt[2];
+    if (k23.x == EMPTY_KEY) return 0;
+    if (k23.y == can) return tab[b].cnt[3];
+    if (k23.y == EMPTY_KEY) return 0;
+    b = b + 1 == nb ? 0 : b + 1;
+  }
+  return 0;
+}
+
 }  // namespace pg
 
 /** Device k-mer table + streaming state (definition shared by kmer_count.cu and pipeline.cu). */
@@ -109,8 +142,9 @@ struct pg_counter {
   uint64_t capacity = 0;      // slots = cap_q << cap_sh
   uint32_t cap_q = 0, cap_sh = 0;
   uint64_t max_distinct = 0;  // keys the caller asked room for
-  uint64_t* keys = nullptr;   // [capacity] canonical k-mer or EMPTY_KEY
-  uint32_t* counts = nullptr; // [capacity]
+  // [capacity / 4] 64-byte buckets (KmerBucket): a lookup normally costs ONE DRAM burst and one latency round
+  pg::KmerBucket* slots = nullptr;
+  uint32_t* d_counts_tmp = nullptr;  // contiguous copy of the counts for the cross-GPU all-reduce
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   // streaming scratch

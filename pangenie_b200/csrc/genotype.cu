@@ -231,36 +231,22 @@ __global__ void __launch_bounds__(256) desc_build_kernel(PanelDev pd, const uint
 // -------------------------------------------------------------------------------------------------
 // fill (src/commands.cpp:113-137, src/kmerparser.cpp:30-49)
 // -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t table_lookup_dev(uint64_t code, uint32_t k, const uint64_t* __restrict__ keys,
-                                                     const uint32_t* __restrict__ counts, uint64_t cap, uint32_t q, uint32_t sh) {
-  const uint64_t rc = revcomp_2bit(code, k);
-  const uint64_t can = code < rc ? code : rc;
-  uint64_t slot = home_slot(can, q, sh);
-  for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
-    const uint64_t cur = keys[slot];
-    if (cur == can) return counts[slot];
-    if (cur == EMPTY_KEY) return 0;
-    slot = slot + 1 == cap ? 0 : slot + 1;
-  }
-  return 0;
-}
-
 __global__ void __launch_bounds__(256) fill_kmer_counts_kernel(const uint64_t* __restrict__ codes, uint64_t n, uint32_t k,
-                                                                const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                                const KmerBucket* __restrict__ slots,
                                                                 uint64_t cap, uint32_t q, uint32_t sh, uint16_t* __restrict__ out) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    out[i] = (uint16_t)table_lookup_dev(codes[i], k, keys, counts, cap, q, sh);  // size_t -> unsigned short (commands.cpp:118,130)
+    out[i] = (uint16_t)table_lookup(codes[i], k, slots, cap, q, sh);  // size_t -> unsigned short (commands.cpp:118,130)
 }
 
 __global__ void __launch_bounds__(256) fill_coverage_kernel(const uint32_t* __restrict__ flank_off, const uint64_t* __restrict__ flank_codes,
-                                                             uint32_t V, uint32_t k, const uint64_t* __restrict__ keys,
-                                                             const uint32_t* __restrict__ counts, uint64_t cap, uint32_t q, uint32_t sh,
+                                                             uint32_t V, uint32_t k, const KmerBucket* __restrict__ slots,
+                                                             uint64_t cap, uint32_t q, uint32_t sh,
                                                              uint64_t peak, uint16_t* __restrict__ coverage) {
   const uint64_t min_cov = peak / 4, max_cov = peak * 4;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
     uint64_t total_cov = 0, total_kmers = 0;
     for (uint32_t f = flank_off[v]; f < flank_off[v + 1]; ++f) {
-      const uint64_t c = table_lookup_dev(flank_codes[f], k, keys, counts, cap, q, sh);
+      const uint64_t c = table_lookup(flank_codes[f], k, slots, cap, q, sh);
       if (c < min_cov || c > max_cov) continue;
       total_cov += c;
       total_kmers += 1;
@@ -946,12 +932,12 @@ static int engine_fill(pg_engine* e, const pg_counter* c, uint64_t peak) {
   cudaEventRecord(e->ev[8], s);
   if (e->K) {
     const int grid = (int)std::min<uint64_t>((e->K + 255) / 256, (uint64_t)e->sm_count * 16);
-    fill_kmer_counts_kernel<<<grid, 256, 0, s>>>(e->kmer_codes.p, e->K, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, e->kmer_counts.p);
+    fill_kmer_counts_kernel<<<grid, 256, 0, s>>>(e->kmer_codes.p, e->K, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, e->kmer_counts.p);
     count_launch();
   }
   if (e->V) {
     const int grid = (int)std::min<uint64_t>(((uint64_t)e->V + 255) / 256, (uint64_t)e->sm_count * 16);
-    fill_coverage_kernel<<<grid, 256, 0, s>>>(e->flank_off.p, e->flank_codes.p, e->V, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, peak, e->coverage.p);
+    fill_coverage_kernel<<<grid, 256, 0, s>>>(e->flank_off.p, e->flank_codes.p, e->V, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, peak, e->coverage.p);
     count_launch();
   }
   PG_CUDA(cudaGetLastError());

@@ -2,9 +2,9 @@
 // (src/jellyfishcounter.hpp:46-68 COUNT/PRIME/UPDATE, src/jellyfishcounter.cpp:26-153).
 //
 // Data layout in HBM
-//   keys  [capacity] u64  canonical 2-bit k-mer (first base most significant) or EMPTY_KEY
-//   counts[capacity] u32  occurrences (jellyfish's counters are effectively unbounded; u32 here)
-//   open addressing, linear probing, home slot = mulhi64(mix64(kmer), capacity), load <= 0.6.
+//   64-byte buckets (KmerBucket, common.cuh): 4 canonical 2-bit k-mers (first base most significant, ~0 = empty),
+//   their 4 u32 counts (jellyfish's counters are effectively unbounded; u32 here) and padding = one DRAM burst.
+//   Bucket-linear probing from a 2-multiply mix of the k-mer, load <= 0.6: a lookup is normally ONE latency round.
 //
 // Text pipeline (per chunk of the read/segment file resident in HBM), all on one stream:
 //   tile_lines_kernel   newline count + last-newline position per 8064-byte tile   (streams the text once)
@@ -225,24 +225,30 @@ __device__ __forceinline__ int block_exscan_max(int v, int* s_warp) {
 // ------------------------------------------------------------------------------------------------
 // table operations
 // ------------------------------------------------------------------------------------------------
+// Slow path of a table operation: `b` is the bucket to (re)examine, position by position with FRESH reads (the
+// snapshot taken by the fast path may be stale after a lost CAS).  On success `slot` = 4*bucket + position.
 template <int OP>
-__device__ __noinline__ bool resolve_slow(uint64_t kmer, uint64_t& slot, uint64_t* keys, uint64_t cap,
-                                             unsigned long long* scalars, uint32_t& inserted) {
-  // continues probing at `slot` (inclusive); returns true if the key is (now) present at `slot`
-  for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
-    uint64_t cur = keys[slot];
-    if (cur == kmer) return true;
-    if (cur == EMPTY_KEY) {
-      if (OP == PG_OP_UPDATE) return false;
-      unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
-                                          (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
-      if (prev == EMPTY_KEY) {
-        ++inserted;
+__device__ __noinline__ bool resolve_slow(uint64_t kmer, uint64_t b, uint64_t& slot, KmerBucket* tab, uint64_t nb,
+                                          unsigned long long* scalars, uint32_t& inserted) {
+  for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tab[b].key[j]);
+      if (cur == EMPTY_KEY) {
+        if (OP == PG_OP_UPDATE) return false;
+        cur = atomicCAS(&tab[b].key[j], (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
+        if (cur == EMPTY_KEY) {
+          ++inserted;
+          slot = 4 * b + j;
+          return true;
+        }
+      }
+      if (cur == kmer) {
+        slot = 4 * b + j;
         return true;
       }
-      if (prev == kmer) return true;
     }
-    slot = slot + 1 == cap ? 0 : slot + 1;
+    b = b + 1 == nb ? 0 : b + 1;
   }
   atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
   return false;
@@ -269,9 +275,8 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], uint32_t i) 
 template <int OP>
 __global__ void __launch_bounds__(CT_THREADS, 4)
 count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, int is_fastq,
-                  const uint32_t* __restrict__ tile_meta, uint32_t k, uint64_t* __restrict__ keys,
-                  uint32_t* __restrict__ counts, uint64_t cap, uint32_t cap_q, uint32_t cap_sh,
-                  unsigned long long* __restrict__ scalars) {
+                  const uint32_t* __restrict__ tile_meta, uint32_t k, KmerBucket* __restrict__ tab,
+                  uint64_t cap, uint32_t cap_q, uint32_t cap_sh, unsigned long long* __restrict__ scalars) {
   __shared__ __align__(16) uint8_t sym[CT_TILE + 2 * SYM_PAD];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
@@ -427,7 +432,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 #pragma unroll 1
     for (int wd = 8; wd < 12; ++wd) {
       const uint32_t xw = active ? sp[wd] : 0x04040404u;
-      uint64_t cn[4], slot[4], key[4];
+      uint64_t cn[4];
       uint32_t vm = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -438,29 +443,48 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
         cn[b] = fwd < rev ? fwd : rev;
         if (run >= k && s0 + (uint32_t)((wd - 8) * 4 + b) < n_owned_syms) vm |= 1u << b;
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        slot[i] = home_slot(cn[i], cap_q, cap_sh);
-        key[i] = ((vm >> i) & 1u) ? keys[slot[i]] : 0;
-      }
       nk += __popc(vm);
+      // two k-mers per round: 2 x 4 keys (two 128-bit loads each) in flight before any is examined
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool v = (vm >> i) & 1u;
-        bool hit = false;
-        if (v) {
-          if (key[i] == cn[i]) hit = true;
-          else if (OP == PG_OP_UPDATE && key[i] == EMPTY_KEY) hit = false;
-          else {
-            if (key[i] != EMPTY_KEY) slot[i] = slot[i] + 1 == cap ? 0 : slot[i] + 1;  // occupied by another key
-            hit = resolve_slow<OP>(cn[i], slot[i], keys, cap, scalars, inserted);
-          }
+      for (int h = 0; h < 4; h += 2) {
+        uint64_t bkt[2];
+        ulonglong2 ka[2], kb[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          bkt[i] = home_slot(cn[h + i], cap_q, cap_sh) >> 2;
+          const bool v = (vm >> (h + i)) & 1u;
+          ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
+          kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
         }
-        if (OP != PG_OP_PRIME) {
-          // warp-aggregated increment: lanes hitting the same slot elect one leader
-          const unsigned long long tag = hit ? (unsigned long long)slot[i] : (~0ull - (unsigned)(tid & 31));
-          const unsigned peers = __match_any_sync(0xffffffffu, tag);
-          if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(counts + slot[i], (uint32_t)__popc(peers));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bool v = (vm >> (h + i)) & 1u;
+          const uint64_t kmer = cn[h + i];
+          bool hit = false;
+          uint64_t slot = 0;
+          if (v) {
+            // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
+            int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+            if (pos >= 0) {
+              hit = true;
+              slot = 4 * bkt[i] + pos;
+            } else {
+              const bool has_empty = ka[i].x == EMPTY_KEY || ka[i].y == EMPTY_KEY || kb[i].x == EMPTY_KEY || kb[i].y == EMPTY_KEY;
+              if (OP == PG_OP_UPDATE && has_empty) {
+                hit = false;
+              } else {
+                uint64_t b2 = bkt[i];
+                if (!has_empty) b2 = b2 + 1 == (cap >> 2) ? 0 : b2 + 1;  // home bucket full of other keys
+                hit = resolve_slow<OP>(kmer, b2, slot, tab, cap >> 2, scalars, inserted);
+              }
+            }
+          }
+          if (OP != PG_OP_PRIME) {
+            // warp-aggregated increment: lanes hitting the same slot elect one leader
+            const unsigned long long tag = hit ? (unsigned long long)slot : (~0ull - (unsigned)(tid & 31));
+            const unsigned peers = __match_any_sync(0xffffffffu, tag);
+            if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&tab[slot >> 2].cnt[slot & 3], (uint32_t)__popc(peers));
+          }
         }
       }
     }
@@ -479,30 +503,16 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 // ------------------------------------------------------------------------------------------------
 // lookups, histogram, sums
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, const uint64_t* __restrict__ keys,
-                                                 const uint32_t* __restrict__ counts, uint64_t cap, uint32_t q, uint32_t sh) {
-  const uint64_t rc = revcomp_2bit(code, k);
-  const uint64_t can = code < rc ? code : rc;
-  uint64_t slot = home_slot(can, q, sh);
-  for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
-    const uint64_t cur = keys[slot];
-    if (cur == can) return counts[slot];
-    if (cur == EMPTY_KEY) return 0;
-    slot = slot + 1 == cap ? 0 : slot + 1;
-  }
-  return 0;
-}
-
 __global__ void lookup_kernel(const uint64_t* __restrict__ codes, uint64_t n, uint32_t k,
-                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t cap,
+                              const KmerBucket* __restrict__ slots, uint64_t cap,
                               uint32_t q, uint32_t sh, uint64_t* __restrict__ out) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    out[i] = table_lookup(codes[i], k, keys, counts, cap, q, sh);
+    out[i] = table_lookup(codes[i], k, slots, cap, q, sh);
   }
 }
 
 constexpr uint32_t HIST_SMEM_BINS = 10240;
-__global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restrict__ counts, uint64_t cap,
+__global__ void __launch_bounds__(512) histogram_kernel(const KmerBucket* __restrict__ tab, uint64_t cap,
                                                         uint64_t max_count, unsigned long long* __restrict__ bins) {
   __shared__ uint32_t s_bins[HIST_SMEM_BINS];
   const bool use_smem = max_count < HIST_SMEM_BINS;
@@ -510,15 +520,10 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
     for (uint32_t i = threadIdx.x; i <= max_count; i += blockDim.x) s_bins[i] = 0;
     __syncthreads();
   }
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
-  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < cap; i += stride) {
-    uint32_t v[4] = {0, 0, 0, 0};
-    if (i + 4 <= cap) {
-      uint4 q = *reinterpret_cast<const uint4*>(counts + i);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-      for (uint64_t j = i; j < cap; ++j) v[j - i] = counts[j];
-    }
+  const uint64_t nb = cap >> 2;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 c = *reinterpret_cast<const uint4*>(tab[b].cnt);  // empty positions hold 0: skipped like zero counts (:125)
+    const uint32_t v[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (v[j] > 0 && v[j] <= max_count) {
@@ -533,16 +538,35 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
   }
 }
 
-__global__ void __launch_bounds__(512) count_sum_kernel(const uint32_t* __restrict__ counts, uint64_t cap,
+__global__ void __launch_bounds__(512) count_sum_kernel(const KmerBucket* __restrict__ tab, uint64_t cap,
                                                         unsigned long long* __restrict__ scalars) {
   unsigned long long s = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) s += counts[i];
+  const uint64_t nb = cap >> 2;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 c = *reinterpret_cast<const uint4*>(tab[b].cnt);
+    s += (unsigned long long)c.x + c.y + c.z + c.w;
+  }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(scalars + SC_COUNT_SUM, s);
 }
 
-__global__ void fill_keys_kernel(uint64_t* keys, uint64_t cap) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) keys[i] = EMPTY_KEY;
+__global__ void fill_slots_kernel(KmerBucket* tab, uint64_t cap) {
+  const uint64_t nq = cap;  // one 16-byte quarter per iteration: 4 quarters per bucket
+  ulonglong2* q = reinterpret_cast<ulonglong2*>(tab);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (uint64_t)gridDim.x * blockDim.x)
+    q[i] = (i & 3) < 2 ? make_ulonglong2(EMPTY_KEY, EMPTY_KEY) : make_ulonglong2(0ull, 0ull);
+}
+
+// counts <-> contiguous u32 array (the cross-GPU all-reduce runs on the contiguous copy)
+__global__ void export_counts_kernel(const KmerBucket* __restrict__ tab, uint64_t cap, uint32_t* __restrict__ out) {
+  const uint64_t nb = cap >> 2;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(out)[b] = *reinterpret_cast<const uint4*>(tab[b].cnt);
+}
+__global__ void import_counts_kernel(KmerBucket* __restrict__ tab, uint64_t cap, const uint32_t* __restrict__ in) {
+  const uint64_t nb = cap >> 2;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x)
+    *reinterpret_cast<uint4*>(tab[b].cnt) = reinterpret_cast<const uint4*>(in)[b];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -578,13 +602,13 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
   tile_scan_kernel<<<1, 1024, 0, c->stream>>>(d_text, n, n_tiles, nlc, lnl, is_fastq, meta, c->d_scalars);
   switch (op) {
     case PG_OP_COUNT:
-      count_tile_kernel<PG_OP_COUNT><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
+      count_tile_kernel<PG_OP_COUNT><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
       break;
     case PG_OP_PRIME:
-      count_tile_kernel<PG_OP_PRIME><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
+      count_tile_kernel<PG_OP_PRIME><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
       break;
     default:
-      count_tile_kernel<PG_OP_UPDATE><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
+      count_tile_kernel<PG_OP_UPDATE><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
   }
   count_launch(3);
   PG_CUDA(cudaGetLastError());
@@ -724,12 +748,10 @@ extern "C" pg_counter* pg_count_new(uint32_t k, uint64_t max_distinct, int devic
     if ((e = cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   }
-  if ((e = cudaMalloc((void**)&c->keys, c->capacity * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
-  if ((e = cudaMalloc((void**)&c->counts, c->capacity * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(counts)", e);
+  if ((e = cudaMalloc((void**)&c->slots, (c->capacity / 4) * sizeof(KmerBucket))) != cudaSuccess) return bail("cudaMalloc(slots)", e);
   if ((e = cudaMalloc((void**)&c->d_scalars, SC_N * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(scalars)", e);
-  fill_keys_kernel<<<1184, 512, 0, c->stream>>>(c->keys, c->capacity);
+  fill_slots_kernel<<<1184, 512, 0, c->stream>>>(c->slots, c->capacity);
   count_launch();
-  cudaMemsetAsync(c->counts, 0, c->capacity * sizeof(uint32_t), c->stream);
   cudaMemsetAsync(c->d_scalars, 0, SC_N * sizeof(unsigned long long), c->stream);
   if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail("table init", e);
   return c;
@@ -739,8 +761,8 @@ extern "C" void pg_count_destroy(pg_counter* c) {
   if (!c) return;
   DeviceGuard g(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->keys) cudaFree(c->keys);
-  if (c->counts) cudaFree(c->counts);
+  if (c->slots) cudaFree(c->slots);
+  if (c->d_counts_tmp) cudaFree(c->d_counts_tmp);
   if (c->d_scalars) cudaFree(c->d_scalars);
   if (c->d_tile_meta) cudaFree(c->d_tile_meta);
   for (int i = 0; i < 2; ++i) {
@@ -830,7 +852,7 @@ static int lookup_codes(const pg_counter* c, const uint64_t* h_codes, uint64_t n
   cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
   cudaMemcpyAsync(d_codes, h_codes, n * 8, cudaMemcpyHostToDevice, s);
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-  lookup_kernel<<<grid, 256, 0, s>>>(d_codes, n, c->k, c->keys, c->counts, c->capacity, c->cap_q, c->cap_sh, d_out);
+  lookup_kernel<<<grid, 256, 0, s>>>(d_codes, n, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, d_out);
   count_launch();
   cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, s);
   e = cudaStreamSynchronize(s);
@@ -890,7 +912,7 @@ extern "C" int pg_count_histogram(const pg_counter* c, uint64_t max_count, uint6
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   cudaEventRecord(e0, c->stream);
-  histogram_kernel<<<148 * 2, 512, 0, c->stream>>>(c->counts, c->capacity, max_count, d_bins);
+  histogram_kernel<<<148 * 2, 512, 0, c->stream>>>(c->slots, c->capacity, max_count, d_bins);
   count_launch();
   cudaEventRecord(e1, c->stream);
   cudaMemcpyAsync(bins, d_bins, (max_count + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
@@ -908,7 +930,7 @@ extern "C" int pg_count_kmer_coverage(const pg_counter* c, uint64_t genome_kmers
   if (!c || !out || genome_kmers == 0) return fail(PG_ERR_ARG, "invalid argument");
   DeviceGuard g(c->device);
   cudaMemsetAsync(c->d_scalars + SC_COUNT_SUM, 0, 8, c->stream);
-  count_sum_kernel<<<148 * 2, 512, 0, c->stream>>>(c->counts, c->capacity, c->d_scalars);
+  count_sum_kernel<<<148 * 2, 512, 0, c->stream>>>(c->slots, c->capacity, c->d_scalars);
   count_launch();
   unsigned long long s = 0;
   cudaMemcpyAsync(&s, c->d_scalars + SC_COUNT_SUM, 8, cudaMemcpyDeviceToHost, c->stream);
@@ -949,12 +971,35 @@ extern "C" uint64_t pg_count_distinct(const pg_counter* c) {
 
 extern "C" uint64_t pg_count_capacity(const pg_counter* c) { return c ? c->capacity : 0; }
 
-extern "C" int pg_count_device_arrays(const pg_counter* c, uint64_t* keys_addr, uint64_t* counts_addr, uint64_t* capacity) {
+extern "C" int pg_count_device_arrays(const pg_counter* c, uint64_t* slots_addr, uint64_t* counts_addr, uint64_t* capacity) {
   clear_error();
   if (!c) return fail(PG_ERR_ARG, "null counter");
-  if (keys_addr) *keys_addr = (uint64_t)(uintptr_t)c->keys;
-  if (counts_addr) *counts_addr = (uint64_t)(uintptr_t)c->counts;
+  DeviceGuard g(c->device);
+  pg_counter* m = const_cast<pg_counter*>(c);
+  if (counts_addr && !m->d_counts_tmp) PG_CUDA(cudaMalloc((void**)&m->d_counts_tmp, c->capacity * sizeof(uint32_t)));
+  if (slots_addr) *slots_addr = (uint64_t)(uintptr_t)c->slots;
+  if (counts_addr) *counts_addr = (uint64_t)(uintptr_t)m->d_counts_tmp;
   if (capacity) *capacity = c->capacity;
+  return PG_OK;
+}
+
+extern "C" int pg_count_export_counts(pg_counter* c) {
+  clear_error();
+  if (!c || !c->d_counts_tmp) return fail(PG_ERR_ARG, "call pg_count_device_arrays first");
+  DeviceGuard g(c->device);
+  export_counts_kernel<<<148 * 4, 512, 0, c->stream>>>(c->slots, c->capacity, c->d_counts_tmp);
+  count_launch();
+  PG_CUDA(cudaStreamSynchronize(c->stream));
+  return PG_OK;
+}
+
+extern "C" int pg_count_import_counts(pg_counter* c) {
+  clear_error();
+  if (!c || !c->d_counts_tmp) return fail(PG_ERR_ARG, "call pg_count_device_arrays first");
+  DeviceGuard g(c->device);
+  import_counts_kernel<<<148 * 4, 512, 0, c->stream>>>(c->slots, c->capacity, c->d_counts_tmp);
+  count_launch();
+  PG_CUDA(cudaStreamSynchronize(c->stream));
   return PG_OK;
 }
 
@@ -965,9 +1010,8 @@ extern "C" int pg_count_clear(pg_counter* c) {
   clear_error();
   if (!c) return fail(PG_ERR_ARG, "null counter");
   DeviceGuard g(c->device);
-  fill_keys_kernel<<<1184, 512, 0, c->stream>>>(c->keys, c->capacity);
+  fill_slots_kernel<<<1184, 512, 0, c->stream>>>(c->slots, c->capacity);
   count_launch();
-  PG_CUDA(cudaMemsetAsync(c->counts, 0, c->capacity * sizeof(uint32_t), c->stream));
   PG_CUDA(cudaMemsetAsync(c->d_scalars, 0, SC_N * sizeof(unsigned long long), c->stream));
   PG_CUDA(cudaStreamSynchronize(c->stream));
   c->kmers_seen = 0;

@@ -71,12 +71,13 @@ class _CudaArray:
 
 
 def counter_tensors(counter):
-    """(keys int64[cap], counts int32[cap]) torch views of a KmerCounter's device arrays (no copy)."""
+    """(slots int64[2*cap], counts int32[cap]) torch views of a KmerCounter's device arrays (no copy).
+    `slots` is the table itself (16-byte slots); `counts` is the contiguous staging array of the all-reduce."""
     import torch
-    kp, cp, cap = counter.device_arrays()
-    keys = torch.as_tensor(_CudaArray(kp, cap, "<i8"), device="cuda")
+    sp, cp, cap = counter.device_arrays()
+    slots = torch.as_tensor(_CudaArray(sp, 2 * cap, "<i8"), device="cuda")
     counts = torch.as_tensor(_CudaArray(cp, cap, "<i4"), device="cuda")
-    return keys, counts
+    return slots, counts
 
 
 def sharded_count(counter, reads, segments, rank: int, world: int, group=None):
@@ -87,13 +88,15 @@ def sharded_count(counter, reads, segments, rank: int, world: int, group=None):
     """
     import torch.distributed as dist
     from . import PG_OP_PRIME, PG_OP_UPDATE
-    keys, counts = counter_tensors(counter)
+    slots, counts = counter_tensors(counter)
     if rank == 0:
         counter.feed(segments, PG_OP_PRIME)
     if world > 1:
-        dist.broadcast(keys, src=0, group=group)
+        dist.broadcast(slots, src=0, group=group)
     if reads is not None and len(reads):
         counter.feed(reads, PG_OP_UPDATE)
     if world > 1:
+        counter.export_counts()
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        counter.import_counts()
     return counter

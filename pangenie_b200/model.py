@@ -131,6 +131,12 @@ class KmerCounter:
                                                                  filename.encode() if filename else None, C.byref(out)))
         return out.value
 
+    def export_counts(self):
+        _check(self._lib, self._lib.pg_count_export_counts(self._h))
+
+    def import_counts(self):
+        _check(self._lib, self._lib.pg_count_import_counts(self._h))
+
     def clear(self):
         _check(self._lib, self._lib.pg_count_clear(self._h))
 

@@ -25,6 +25,9 @@ bench_h64_minb)
 ncu_h64)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"skeleton_kernel|block_kernel" -s 3 -c 2 -o $out/prof_h64_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload h64s > $out/ncu_h64_$tag.out 2>&1; tail -3 $out/ncu_h64_$tag.out;;
+ncu_count_big)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"count_tile_kernel" -s 14 -c 1 -o $out/prof_countbig_$tag \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload cfg3s > $out/ncu_countbig_$tag.out 2>&1; tail -3 $out/ncu_countbig_$tag.out;;
 ncu_count)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"count_tile_kernel" -s 3 -c 2 -o $out/prof_count_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/ncu_count_$tag.out 2>&1; tail -3 $out/ncu_count_$tag.out;;
