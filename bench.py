@@ -60,6 +60,7 @@ class ClockSampler:
 
     def __init__(self, device: int):
         self.device, self.sm, self.reasons, self.max_sm = device, [], set(), None
+        self.period = float(os.environ.get("PG_BENCH_SAMPLE_PERIOD", "0.1"))
         self._stop = threading.Event()
         self.t = None
 
@@ -76,19 +77,23 @@ class ClockSampler:
                     pass
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = pynvml.nvmlDeviceGetCurrentClocksEventReasons if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            for _ in range(3):  # the first NVML queries of a process are slow (tens of ms): keep them out of the timed region
+                pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons_fn(h)
 
             def loop():
                 while not self._stop.is_set():
                     try:
                         self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
-                            else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        r = reasons_fn(h)
                         for bit, name in self.REASONS.items():
                             if r & bit:
                                 self.reasons.add(name)
                     except Exception:
                         pass
-                    self._stop.wait(0.05)
+                    self._stop.wait(self.period)
             self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
         except Exception as e:  # no NVML: report that instead of inventing numbers
@@ -245,7 +250,7 @@ def run_strong(args, rank, world, local, W, K, config):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PG_BENCH_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
@@ -334,6 +339,14 @@ def main():
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
+    # the same K steps once more WITHOUT the NVML sampler thread: shows what the sampling itself costs (reported, not used)
+    barrier()
+    t0u = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()
+        eng.run_resident(reads_d, segs_d, k=wl.k, **kw)
+    barrier()
+    clocks["ms_per_step_without_sampler"] = 1e3 * (time.perf_counter() - t0u) / K
     eng.fetch()
     tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -282,6 +282,7 @@ typedef struct {
   uint64_t kmers_counted;      /* k-mers streamed through the UPDATE/COUNT pass                     */
   uint64_t text_bytes;         /* read text bytes streamed                                          */
   double prime_ms;             /* PRIME pass over the segment file                                  */
+  uint64_t hmm_scan_used;      /* 1 if the checkpoints came from the parallel-in-time scan path (P <= 9) */
 } pg_timings;
 int pg_engine_timings(const pg_engine* e, pg_timings* out);
 

@@ -99,6 +99,7 @@ class PgTimings(C.Structure):
         ("kmers_counted", C.c_uint64),
         ("text_bytes", C.c_uint64),
         ("prime_ms", C.c_double),
+        ("hmm_scan_used", C.c_uint64),
     ]
 
 

@@ -4,7 +4,9 @@
 // fill_read_kmercounts (src/commands.cpp:76-152) and the GT/GQ post-processing of Graph::write_genotypes
 // (src/graph.cpp:206-240).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -12,8 +14,27 @@
 
 #include "common.cuh"
 #include "hmm_kernels.cuh"
+#include "hmm_scan.cuh"
 
 namespace pg {
+
+// PG_TRACE=1: host wall-clock of the phases of one call on stderr (where does the time between kernels go?)
+struct HostTrace {
+  bool on;
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostTrace(const char* n) : name(n) {
+    static const bool v = [] { const char* e = getenv("PG_TRACE"); return e && e[0] == '1'; }();
+    on = v;
+    t0 = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pg trace] %s: %s %.3f ms\n", name, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 // -------------------------------------------------------------------------------------------------
 // device views
@@ -488,6 +509,12 @@ struct pg_engine {
   DevBuf<int16_t> genotype;
   DevBuf<ChromCols> chroms;
   DevBuf<uint2> jobs;
+  // parallel-in-time checkpoint path (hmm_scan.cuh)
+  DevBuf<TJob> tjobs;
+  DevBuf<ScanChrom> scan_chroms;
+  DevBuf<double> scan_mats;
+  DevBuf<int32_t> scan_expo;
+  DevBuf<uint32_t> seq_flags;
   std::vector<uint8_t> h_is_column;
   pg_counter* cached_counter = nullptr;  // reused across pg_engine_run_resident calls
 };
@@ -542,6 +569,7 @@ extern "C" void pg_engine_destroy(pg_engine* e) {
     e->unique_kmers.release(); e->coverage_out.release(); e->col_variant.release(); e->col_cbeg.release();
     e->col_cend.release(); e->variant_col.release(); e->work_counter.release(); e->quality.release();
     e->genotype.release(); e->chroms.release(); e->jobs.release();
+    e->tjobs.release(); e->scan_chroms.release(); e->scan_mats.release(); e->scan_expo.release(); e->seq_flags.release();
   }
   delete e;
 }
@@ -761,8 +789,16 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   // host: column list, chromosome ranges, blocks, jobs
   std::vector<uint32_t> col_variant, col_cbeg, col_cend, variant_col(std::max<uint32_t>(V, 1), 0);
   std::vector<ChromCols> chroms(e->n_chrom);
+  // checkpoint schedule: P <= 9 propagates a basis through every block in parallel (hmm_scan.cuh), larger path
+  // sets walk the chains sequentially (skeleton_kernel).  PG_SKELETON=seq|scan and PG_HMM_B are tuning/test knobs.
+  const char* skel_env = getenv("PG_SKELETON");
+  const bool scan_candidate = P <= (uint32_t)SCAN_CPL && !(skel_env && skel_env[0] == 's' && skel_env[1] == 'e');
   uint32_t B = 64;
-  if (P <= 12) B = 256; else if (P <= 36) B = 128;
+  if (scan_candidate) B = 64; else if (P <= 12) B = 256; else if (P <= 36) B = 128;
+  if (const char* be = getenv("PG_HMM_B")) {
+    const long v = atol(be);
+    if (v >= 2 && v <= HMM_BMAX) B = (uint32_t)v;
+  }
   std::vector<uint2> jobs;
   uint32_t nblk = 0;
   for (uint32_t c = 0; c < e->n_chrom; ++c) {
@@ -815,7 +851,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   PG_CUDA(cudaMemsetAsync(e->work_counter.p, 0, 16, s));
 
   cudaEventRecord(e->ev[2], s);
-  uint64_t block_launches = 0;
+  uint64_t block_launches = 0, scan_used = 0;
   if (C) {
     TransParams tp{prm->recombrate, prm->effective_N, prm->uniform};
     const int grid = (int)std::min<uint64_t>(((uint64_t)C * 32 + 255) / 256, (uint64_t)e->sm_count * 16);
@@ -831,8 +867,63 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     cp.ckpt_fwd = e->ckpt_fwd.p; cp.ckpt_bwd = e->ckpt_bwd.p; cp.tot_fwd = e->tot_fwd.p; cp.tot_bwd = e->tot_bwd.p;
     cp.post = e->post.p; cp.gl_off = e->gl_off.p; cp.allele_off = e->allele_off.p; cp.allele_ids = e->allele_ids.p;
     cp.work_counter = e->work_counter.p; cp.jobs = e->jobs.p; cp.n_jobs = (uint32_t)jobs.size();
+    cp.seq_flags = nullptr;
     bool need_skel = false;
     for (auto& ch : chroms) need_skel |= ch.n_blocks > 1;
+    // ---- transfer jobs of the scan path
+    const bool use_scan = scan_candidate && need_skel;
+    ScanParams sp;
+    memset(&sp, 0, sizeof(sp));
+    if (use_scan) {
+      const uint32_t NB = P * (P + 1) / 2;
+      std::vector<TJob> tj;
+      std::vector<ScanChrom> sch(e->n_chrom);
+      for (uint32_t c = 0; c < e->n_chrom; ++c) {
+        const ChromCols& ch = chroms[c];
+        sch[c].n_tj = ch.n_blocks > 1 ? ch.n_blocks - 1 : 0;
+        sch[c].pad = 0;
+        sch[c].tj_begin[0] = (uint32_t)tj.size();
+        for (uint32_t k = 0; k + 1 < ch.n_blocks; ++k) {  // forward: block k -> F at its last column
+          TJob j;
+          memset(&j, 0, sizeof(j));
+          const int cb = (int)(ch.col_begin + k * B), ce = cb + (int)B;
+          j.chrom = c; j.dir = 0;
+          j.t_first = k == 0 ? cb + 1 : cb;
+          j.n_steps = (uint32_t)(ce - j.t_first);
+          j.out_blk = ch.blk_begin + k + 1;
+          tj.push_back(j);
+        }
+        sch[c].tj_begin[1] = (uint32_t)tj.size();
+        for (uint32_t k = ch.n_blocks; k-- > 1;) {  // backward: block k -> Y at its first column
+          TJob j;
+          memset(&j, 0, sizeof(j));
+          const int cb = (int)(ch.col_begin + k * B);
+          const int ce = std::min<int>(cb + (int)B, (int)ch.col_end);
+          j.chrom = c; j.dir = 1;
+          j.t_first = k + 1 == ch.n_blocks ? (int)ch.col_end - 2 : ce - 1;
+          j.n_steps = (uint32_t)(j.t_first - cb + 1);
+          j.out_blk = ch.blk_begin + k - 1;
+          tj.push_back(j);
+        }
+      }
+      constexpr uint32_t G = 32 / SCAN_CPL;
+      sp.n_tj = (uint32_t)tj.size();
+      sp.n_groups = (NB + G - 1) / G;
+      sp.n_items = sp.n_tj * sp.n_groups;
+      sp.mat_stride = (NB * NB + 1u) & ~1u;
+      PG_TRY(e->tjobs.reserve(tj.size()));
+      PG_TRY(e->scan_chroms.reserve(e->n_chrom));
+      PG_TRY(e->scan_mats.reserve((size_t)sp.n_tj * sp.mat_stride));
+      PG_TRY(e->scan_expo.reserve((size_t)sp.n_tj * NB));
+      PG_TRY(e->seq_flags.reserve(e->n_chrom));
+      PG_CUDA(cudaMemcpyAsync(e->tjobs.p, tj.data(), tj.size() * sizeof(TJob), cudaMemcpyHostToDevice, s));
+      PG_CUDA(cudaMemcpyAsync(e->scan_chroms.p, sch.data(), sch.size() * sizeof(ScanChrom), cudaMemcpyHostToDevice, s));
+      PG_CUDA(cudaMemsetAsync(e->seq_flags.p, 0, e->n_chrom * sizeof(uint32_t), s));
+      PG_CUDA(cudaStreamSynchronize(s));  // tj / sch are stack-owned host vectors
+      sp.tjobs = e->tjobs.p; sp.mats = e->scan_mats.p; sp.expo = e->scan_expo.p; sp.chroms = e->scan_chroms.p;
+      sp.seq_flags = e->seq_flags.p;
+      cp.seq_flags = e->seq_flags.p;
+    }
     int occ = 1;
 #define PG_OCC(L, CPL, RPW, NT) occ = occupancy_of<L, CPL, RPW, NT>();
     switch (cfg.id) {
@@ -862,6 +953,13 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
       case 4: PG_LAUNCH(4, 17, 1, 288, SK, BL) break;          \
       case 5: PG_LAUNCH(8, 17, 2, 544, SK, BL) break;          \
       default: PG_LAUNCH(32, 9, 8, 1024, SK, BL) break;        \
+    }
+    if (use_scan) {
+      basis_kernel<SCAN_CPL><<<(sp.n_items + BASIS_WARPS - 1) / BASIS_WARPS, BASIS_WARPS * 32, 0, s>>>(cp, sp);
+      scan_kernel<SCAN_CPL><<<dim3(e->n_chrom, 2), SCAN_THREADS, 0, s>>>(cp, sp);
+      count_launch(2);
+      PG_CUDA(cudaGetLastError());
+      scan_used = 1;
     }
     if (need_skel) {
       PG_DISPATCH(true, false)
@@ -902,6 +1000,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]); e->tm.hmm_blocks_ms = ms;
   cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]); e->tm.finalize_ms = ms;
   e->tm.hmm_block_launches = block_launches;
+  e->tm.hmm_scan_used = scan_used;
   return PG_OK;
 }
 
@@ -1078,6 +1177,7 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
 static int engine_after_count(pg_engine* e, const pg_counter* c, bool largest_peak, double regularization,
                               const pg_hmm_params* params, uint64_t* kmer_abundance_peak) {
   uint64_t peak = 0;
+  HostTrace tr("after_count");
   cudaEvent_t h0, h1;
   cudaEventCreate(&h0);
   cudaEventCreate(&h1);
@@ -1097,9 +1197,12 @@ static int engine_after_count(pg_engine* e, const pg_counter* c, bool largest_pe
     pg_probtable* t;
     ~TGuard() { pg_probtable_free(t); }
   } tguard{&table};
+  tr.mark("histogram+table");
   PG_TRY(engine_fill(e, c, peak));
+  tr.mark("fill");
   const double fill_ms = e->tm.fill_ms;
   PG_TRY(engine_hmm(e, &table, params));
+  tr.mark("hmm");
   e->tm.fill_ms = fill_ms;
   e->tm.histogram_ms = hms;
   return PG_OK;
@@ -1119,6 +1222,7 @@ extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_
   if (!e->has_codes) return fail(PG_ERR_ARG, "call pg_engine_load first");
   const uint64_t l0 = g_launches;
   memset(&e->tm, 0, sizeof(e->tm));
+  HostTrace tr("run_resident");
   const uint64_t max_distinct = d_segments ? std::max<uint64_t>(segments_len, 1024) : std::max<uint64_t>(hash_size, 1024);
   if (e->cached_counter && (e->cached_counter->k != k || e->cached_counter->max_distinct < max_distinct)) {
     pg_count_destroy(e->cached_counter);
@@ -1130,18 +1234,22 @@ extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_
   } else {
     PG_TRY(pg_count_clear(e->cached_counter));
   }
+  tr.mark("clear");
   pg_counter* c = e->cached_counter;
   if (d_segments) {
     PG_TRY(pg_count_feed_device(c, d_segments, segments_len, PG_OP_PRIME));
     e->tm.prime_ms = c->last_feed_ms;
+    tr.mark("prime");
     PG_TRY(pg_count_feed_device(c, d_reads, reads_len, PG_OP_UPDATE));
   } else {
     PG_TRY(pg_count_feed_device(c, d_reads, reads_len, PG_OP_COUNT));
   }
+  tr.mark("count");
   e->tm.count_ms = c->last_feed_ms;
   e->tm.kmers_counted = c->kmers_seen;
   e->tm.text_bytes = reads_len;
   PG_TRY(engine_after_count(e, c, d_segments != nullptr, regularization, params, kmer_abundance_peak));
+  tr.mark("after_count");
   e->tm.kernel_launches = g_launches - l0;
   return PG_OK;
 }

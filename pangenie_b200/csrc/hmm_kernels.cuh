@@ -69,6 +69,7 @@ struct ChainParams {
   uint32_t* work_counter;      // phase-2 job queue head
   const uint2* jobs;           // [n_jobs] (chromosome, block)
   uint32_t n_jobs;
+  const uint32_t* seq_flags;   // skeleton_kernel: if non-null, only chromosomes with a non-zero flag are walked (hmm_scan.cuh)
 };
 
 __device__ __forceinline__ double pow2_scale_of(double T) {
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
   ch.init(sm, &p);
   const ChromCols cc = p.chroms[blockIdx.x];
   if (cc.n_blocks <= 1) return;
+  if (p.seq_flags && !p.seq_flags[blockIdx.x]) return;  // checkpoints already produced by the scan path
   for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;  // zero padding beyond P
   ch.sync();
   const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
@@ -595,7 +597,9 @@ __global__ void __launch_bounds__(NT, MINB) block_kernel(const ChainParams p) {
       ch.load_cells(bcol, !(sm->tf[t - cb] > 0.0), ureg);  // issued first: overlaps the writer and the reductions
       if (pending_slot >= 0 && ch.w == pending_w) ch.write_posterior(pending_slot, pending_wbuf);
       const double T = ch.total(cur);
-      if (threadIdx.x == 0 && t + 1 < c1) p.tot_bwd[t + 1] = T;
+      // tot_bwd[ce] belongs to the block that computed column ce: a checkpoint may carry a different power-of-two
+      // scale than that block's own column (hmm_scan.cuh), and finalize_kernel needs the owner's exponent
+      if (threadIdx.x == 0 && t + 1 < ce) p.tot_bwd[t + 1] = T;
       if (t - 2 >= cb) {  // pull the forward column needed two steps from now towards L2
         const char* nxt = reinterpret_cast<const char*>(bcol - 2 * PP);
         for (size_t o = (size_t)threadIdx.x * 128; o < PP * 8; o += (size_t)NT * 128) prefetch_l2(nxt + o);

@@ -82,6 +82,55 @@ def test_hmm_multi_chromosome_blocks_and_checkpoints(engine, oracle):
         assert_results_close(g, w, label=f"chromosome {i}")
 
 
+@pytest.mark.parametrize("n_paths,block", [(9, 64), (9, 7), (4, 16), (2, 2), (7, 33)])
+def test_scan_and_sequential_checkpoints_agree(engine, oracle, monkeypatch, n_paths, block):
+    """P <= 9: checkpoints come from the parallel-in-time basis/scan kernels (csrc/hmm_scan.cuh); PG_SKELETON=seq forces
+    the sequential skeleton walk.  Both must match the oracle, and each other far below the parity tolerance."""
+    rng = np.random.default_rng(77 + n_paths + block)
+    panels = [random_panel(rng, n, n_paths, max_alleles=4, undefined_frac=0.1, ref_only_frac=0.05) for n in (700, 65, 130)]
+    table = _table()
+    monkeypatch.setenv("PG_HMM_B", str(block))
+    for normalize in (True, False):
+        kw = dict(recombrate=1.26, effective_N=25000.0 if block % 2 else 1e-5, normalize=normalize)
+        want = oracles.cpu_hmm_run(oracle, "pgo_", panels, table, **kw)
+        monkeypatch.setenv("PG_SKELETON", "scan")
+        got_scan = engine.hmm_run(panels, table, **kw)
+        assert engine.timings()["hmm_scan_used"] == 1
+        monkeypatch.setenv("PG_SKELETON", "seq")
+        got_seq = engine.hmm_run(panels, table, **kw)
+        assert engine.timings()["hmm_scan_used"] == 0
+        for i, (a, b, w) in enumerate(zip(got_scan, got_seq, want)):
+            assert_results_close(a, w, label=f"scan, chromosome {i}")
+            assert_results_close(b, w, label=f"seq, chromosome {i}")
+            np.testing.assert_allclose(a.likelihoods, b.likelihoods, rtol=1e-11, atol=1e-300)
+
+
+def test_scan_falls_back_on_zero_totals(engine, oracle, monkeypatch):
+    """Emission tables with exact zeros kill basis chains (and sometimes the real chain: the reference's uniform
+    replacement, hmm.cpp:258-260) -> the flagged chromosome is recomputed sequentially; results stay exact."""
+    rng = np.random.default_rng(123)
+    probs = pg.ProbabilityTable(0, 1, 21, 0.0)
+    probs.modify_probability(0, 10, 0.0, 1.0, 0.0)
+    probs.modify_probability(0, 20, 0.0, 0.0, 1.0)
+    probs.modify_probability(0, 0, 1.0, 0.0, 0.0)
+    b = pg.PanelBuilder()
+    pos = 1000
+    for i in range(40):
+        pos += int(rng.integers(100, 2000))
+        al = rng.integers(0, 2, size=6)
+        al[0], al[1] = 0, 1
+        v = b.add_variant(pos, al)
+        c = [(10, 10), (20, 0), (0, 20), (10, 0)][int(rng.integers(0, 4))]
+        b.insert_kmer(v, c[0], [0]); b.insert_kmer(v, c[1], [1])
+    panel = b.build()
+    monkeypatch.setenv("PG_HMM_B", "4")
+    monkeypatch.setenv("PG_SKELETON", "scan")
+    kw = dict(recombrate=1.26, effective_N=25000.0)
+    want = oracles.cpu_hmm_run(oracle, "pgo_", [panel], probs, **kw)[0]
+    got = engine.hmm_run([panel], probs, **kw)[0]
+    assert_results_close(got, want, label="zero-emission chain")
+
+
 def test_hmm_options(engine, oracle):
     rng = np.random.default_rng(9)
     panel = random_panel(rng, 200, 8, max_alleles=3)
