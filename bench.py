@@ -60,7 +60,8 @@ class ClockSampler:
 
     def __init__(self, device: int):
         self.device, self.sm, self.reasons, self.max_sm = device, [], set(), None
-        self.period = float(os.environ.get("PG_BENCH_SAMPLE_PERIOD", "0.1"))
+        self.period = float(os.environ.get("PG_BENCH_SAMPLE_PERIOD", "0.2"))
+        self.query_ms = []
         self._stop = threading.Event()
         self.t = None
 
@@ -86,8 +87,10 @@ class ClockSampler:
             def loop():
                 while not self._stop.is_set():
                     try:
+                        tq = time.perf_counter()
                         self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                         r = reasons_fn(h)
+                        self.query_ms.append(1e3 * (time.perf_counter() - tq))
                         for bit, name in self.REASONS.items():
                             if r & bit:
                                 self.reasons.add(name)
@@ -104,7 +107,8 @@ class ClockSampler:
         if self.t:
             self.t.join(timeout=1)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "nvml_query_ms_max": max(self.query_ms) if self.query_ms else None}
 
 
 def measured_peak_gbs():
@@ -250,7 +254,7 @@ def run_strong(args, rank, world, local, W, K, config):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PG_BENCH_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
@@ -324,6 +328,10 @@ def main():
     segs_d = segs_h.cuda()
     results = eng.load(wl.panels)
     for _ in range(W):
+        eng.run_resident(reads_d, segs_d, k=wl.k, **kw)
+    # a step lasts a few ms: keep warming up until the clocks have ramped (at least 0.3 s of work, still untimed)
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < float(os.environ.get("PG_BENCH_WARM_S", "0.3")):
         eng.run_resident(reads_d, segs_d, k=wl.k, **kw)
     sampler = ClockSampler(local)
     barrier()

@@ -135,6 +135,12 @@ __device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, cons
 
 }  // namespace pg
 
+struct pg_counter;
+namespace pg {
+/** PRIME (segments) + UPDATE (reads) enqueued back to back, one wait at the end (kmer_count.cu). */
+int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len);
+}
+
 /** Device k-mer table + streaming state (definition shared by kmer_count.cu and pipeline.cu). */
 struct pg_counter {
   int device = 0;
@@ -148,13 +154,22 @@ struct pg_counter {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   // streaming scratch
-  char* d_stage[2] = {nullptr, nullptr};
-  char* h_stage[2] = {nullptr, nullptr};
-  cudaEvent_t stage_free[2] = {nullptr, nullptr};   // kernel finished reading d_stage[i]
-  cudaEvent_t stage_ready[2] = {nullptr, nullptr};  // H2D into d_stage[i] finished
+  static constexpr int NSTAGE = 4;                  // staging ring: copies run ahead of the counting kernels
+  char* d_stage[NSTAGE] = {};
+  char* h_stage[NSTAGE] = {};
+  cudaEvent_t stage_free[NSTAGE] = {};   // kernel finished reading d_stage[i]
+  cudaEvent_t stage_ready[NSTAGE] = {};  // H2D into d_stage[i] finished
+  int stage_next = 0;                    // ring position (persists across feeds so consecutive feeds overlap)
   uint32_t* d_tile_meta = nullptr;                  // per-tile scan scratch
   size_t tile_meta_cap = 0;
   unsigned long long* d_scalars = nullptr;          // [0]=distinct, [1]=error flags, [2]=carry state, [3]=kmers seen
   uint64_t kmers_seen = 0;
   double last_feed_ms = 0.0;
+  // kept across calls: steady-state calls make no cudaMalloc / cudaFree / event creation (those serialise on the
+  // driver's resource-manager lock, e.g. behind a concurrent NVML query)
+  unsigned long long* d_bins = nullptr;  // histogram bins
+  size_t d_bins_cap = 0;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // timing events of the last feed / histogram
+  cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;  // timing events of a PRIME pass enqueued together with its UPDATE pass
+  double last_prime_ms = 0.0;
 };

@@ -1129,6 +1129,7 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   if (!e || !in || !panels || !params || !results) return fail(PG_ERR_ARG, "null argument");
   const uint64_t l0 = g_launches;
   memset(&e->tm, 0, sizeof(e->tm));
+  HostTrace tr("genotype_run");
   // 1) count (src/commands.cpp:829-833); the table and its staging buffers are kept across calls
   const uint64_t max_distinct = in->segments ? std::max<uint64_t>(in->segments_len, 1024) : std::max<uint64_t>(in->hash_size, 1024);
   if (e->cached_counter && (e->cached_counter->k != in->k || e->cached_counter->max_distinct < max_distinct)) {
@@ -1141,17 +1142,18 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   } else {
     PG_TRY(pg_count_clear(e->cached_counter));
   }
+  tr.mark("clear");
   pg_counter* c = e->cached_counter;
   if (in->segments) {
-    PG_TRY(pg_count_feed(c, in->segments, in->segments_len, PG_OP_PRIME));
-    e->tm.prime_ms = c->last_feed_ms;
-    PG_TRY(pg_count_feed(c, in->reads, in->reads_len, PG_OP_UPDATE));
+    PG_TRY(count_prime_update(c, in->segments, in->segments_len, in->reads, in->reads_len));
+    e->tm.prime_ms = c->last_prime_ms;
   } else {
     PG_TRY(pg_count_feed(c, in->reads, in->reads_len, PG_OP_COUNT));
   }
   e->tm.count_ms = c->last_feed_ms;
   e->tm.kmers_counted = c->kmers_seen;
   e->tm.text_bytes = in->reads_len;
+  tr.mark("count");
   // 2) histogram peak (:840); largest_peak == count_only_graph
   uint64_t peak = 0;
   PG_TRY(pg_count_compute_histogram(c, 10000, in->segments != nullptr, in->histogram_path, &peak));
@@ -1163,12 +1165,17 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
     pg_probtable* t;
     ~TGuard() { pg_probtable_free(t); }
   } tguard{&table};
+  tr.mark("histogram+table");
   // 4) fill + 5) HMM, panel uploaded once
   PG_TRY(engine_load_panels(e, n_chrom, panels, results, false, true));
+  tr.mark("load_panels");
   PG_TRY(engine_fill(e, c, peak));
+  tr.mark("fill");
   PG_TRY(engine_hmm(e, &table, params));
+  tr.mark("hmm");
   PG_TRY(engine_fetch_counts(e, n_chrom, panels));
   PG_TRY(engine_fetch_results(e, n_chrom, panels, results));
+  tr.mark("fetch");
   e->tm.kernel_launches = g_launches - l0;
   return PG_OK;
 }
@@ -1178,17 +1185,13 @@ static int engine_after_count(pg_engine* e, const pg_counter* c, bool largest_pe
                               const pg_hmm_params* params, uint64_t* kmer_abundance_peak) {
   uint64_t peak = 0;
   HostTrace tr("after_count");
-  cudaEvent_t h0, h1;
-  cudaEventCreate(&h0);
-  cudaEventCreate(&h1);
+  cudaEvent_t h0 = c->ev_t0, h1 = c->ev_t1;
   cudaEventRecord(h0, c->stream);
   int st = pg_count_compute_histogram(c, 10000, largest_peak, nullptr, &peak);
   cudaEventRecord(h1, c->stream);
   cudaEventSynchronize(h1);
   float hms = 0;
   cudaEventElapsedTime(&hms, h0, h1);
-  cudaEventDestroy(h0);
-  cudaEventDestroy(h1);
   if (st != PG_OK) return st;
   if (kmer_abundance_peak) *kmer_abundance_peak = peak;
   pg_probtable table;
@@ -1237,10 +1240,8 @@ extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_
   tr.mark("clear");
   pg_counter* c = e->cached_counter;
   if (d_segments) {
-    PG_TRY(pg_count_feed_device(c, d_segments, segments_len, PG_OP_PRIME));
-    e->tm.prime_ms = c->last_feed_ms;
-    tr.mark("prime");
-    PG_TRY(pg_count_feed_device(c, d_reads, reads_len, PG_OP_UPDATE));
+    PG_TRY(count_prime_update(c, d_segments, segments_len, d_reads, reads_len));
+    e->tm.prime_ms = c->last_prime_ms;
   } else {
     PG_TRY(pg_count_feed_device(c, d_reads, reads_len, PG_OP_COUNT));
   }

@@ -28,7 +28,8 @@ constexpr int CT_THREADS = 256;                       // threads per counting CT
 constexpr int CT_TILE = CT_THREADS * 16;              // bytes loaded per tile (one uint4 per thread)
 constexpr int CT_HALO = 128;                          // look-ahead so k-mers may span tiles / chunks
 constexpr int CT_ADV = CT_TILE - CT_HALO;             // tile advance (multiple of 16)
-constexpr uint64_t CHUNK_BYTES = 64ull << 20;         // streaming chunk (multiple of 16)
+constexpr uint64_t CHUNK_BYTES = 64ull << 20;         // chunk of device-resident text processed per launch set (multiple of 16)
+constexpr uint64_t STAGE_BYTES = 16ull << 20;         // host text is streamed through a ring of staging buffers of this size
 constexpr int SYM_PAD = 64;
 
 // scalars[] slots
@@ -225,17 +226,16 @@ __device__ __forceinline__ int block_exscan_max(int v, int* s_warp) {
 // ------------------------------------------------------------------------------------------------
 // table operations
 // ------------------------------------------------------------------------------------------------
-// Slow path of a table operation: `b` is the bucket to (re)examine, position by position with FRESH reads (the
-// snapshot taken by the fast path may be stale after a lost CAS).  On success `slot` = 4*bucket + position.
+// Slow path of an INSERTING operation (PRIME / COUNT): `b` is the bucket to (re)examine, position by position with
+// FRESH reads (the snapshot taken by the fast path may be stale after a lost CAS).  On success `slot` = 4*bucket + pos.
 template <int OP>
-__device__ __noinline__ bool resolve_slow(uint64_t kmer, uint64_t b, uint64_t& slot, KmerBucket* tab, uint64_t nb,
-                                          unsigned long long* scalars, uint32_t& inserted) {
+__device__ __noinline__ bool resolve_insert(uint64_t kmer, uint64_t b, uint64_t& slot, KmerBucket* tab, uint64_t nb,
+                                            unsigned long long* scalars, uint32_t& inserted) {
   for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
       unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tab[b].key[j]);
       if (cur == EMPTY_KEY) {
-        if (OP == PG_OP_UPDATE) return false;
         cur = atomicCAS(&tab[b].key[j], (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
         if (cur == EMPTY_KEY) {
           ++inserted;
@@ -254,30 +254,70 @@ __device__ __noinline__ bool resolve_slow(uint64_t kmer, uint64_t b, uint64_t& s
   return false;
 }
 
-// ------------------------------------------------------------------------------------------------
-// pass 3: classify, compact, roll, probe
-// ------------------------------------------------------------------------------------------------
-// 4 bytes -> 4 symbols (0-3 base code, 4 = not a base), SIMD within a 32-bit word.
-__device__ __forceinline__ uint32_t codes4(uint32_t w) {
-  const uint32_t c = ((w >> 1) ^ (w >> 2)) & 0x03030303u;  // A/a=0 C/c=1 G/g=2 T/t=3
-  const uint32_t u = w & 0xDFDFDFDFu;                      // fold case
-  const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
-  return (c & ok) | (0x04040404u & ~ok);
+// Slow path of a lookup in a STATIC table (UPDATE): the home bucket was full of other keys; walk the following buckets
+// with one 2 x 128-bit snapshot per bucket (one latency round per bucket instead of one per key).
+__device__ __noinline__ bool resolve_lookup(uint64_t kmer, uint64_t b, uint64_t& slot, const KmerBucket* tab, uint64_t nb,
+                                            unsigned long long* scalars) {
+  for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
+    const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&tab[b].key[0]);
+    const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&tab[b].key[2]);
+    const int pos = ka.x == kmer ? 0 : ka.y == kmer ? 1 : kb.x == kmer ? 2 : kb.y == kmer ? 3 : -1;
+    if (pos >= 0) {
+      slot = 4 * b + pos;
+      return true;
+    }
+    if (kb.y == EMPTY_KEY) return false;  // positions fill left to right: an empty last position ends the search
+    b = b + 1 == nb ? 0 : b + 1;
+  }
+  atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
+  return false;
 }
 
-__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], uint32_t i) {
+// ------------------------------------------------------------------------------------------------
+// pass 3: classify, pack, extract, probe
+// ------------------------------------------------------------------------------------------------
+// 16 text bytes -> 16 two-bit codes, MSB first (byte 0 in bits 31..30), and their "not a base" flags (byte 0 in bit 15).
+// A/a=0 C/c=1 G/g=2 T/t=3 (jellyfish mer_dna::code); the code of a non-base is irrelevant (its flag kills the window).
+__device__ __forceinline__ void pack16(const uint32_t (&w)[4], uint32_t& codes, uint32_t& notbase) {
+  codes = 0;
+  notbase = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t c = ((w[i] >> 1) ^ (w[i] >> 2)) & 0x03030303u;
+    codes = (codes << 8) | ((c * 0x40100401u) >> 24);  // gathers the four 2-bit fields, first byte highest
+    const uint32_t u = w[i] & 0xDFDFDFDFu;             // fold case
+    const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+    notbase = (notbase << 4) | ((((~ok) & 0x01010101u) * 0x08040201u) >> 24 & 0xfu);
+  }
+}
+
+// ORs the `len` (1..32) right-aligned bits `v` into the MSB-first bit stream `dst` at bit position `bitpos`.
+__device__ __forceinline__ void stream_or(uint32_t* dst, uint32_t bitpos, uint32_t v, uint32_t len) {
+  const uint64_t x = ((uint64_t)v << (64u - len)) >> (bitpos & 31u);
+  const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+  if (hi) atomicOr(dst + (bitpos >> 5), hi);
+  if (lo) atomicOr(dst + (bitpos >> 5) + 1, lo);
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], uint32_t i) {  // selects, no local-memory indexing
   const uint32_t x = i < 8 ? (i < 4 ? w[0] : w[1]) : (i < 12 ? w[2] : w[3]);
   return (x >> (8 * (i & 3))) & 0xff;
 }
 
-// Code size matters here: the first version of this kernel was 12k SASS instructions and spent 67% of its
-// stall samples waiting for instruction fetch.  Loops are kept rolled, slow paths are not inlined.
+constexpr int PK_WORDS = CT_TILE / 16 + 4;  // packed codes: 16 symbols per word (+ read-ahead padding)
+constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per word
+
+// Per tile: every thread classifies its 16 bytes (which lie in a sequence line?), the emitted symbols are compacted
+// into a 2-bit packed stream in shared memory, and k-mer START positions are dealt to the threads round-robin, so all
+// lanes stay busy whatever fraction of the text is sequence (FASTQ: ~48%).  A k-mer is one funnel-shift extraction from
+// the packed stream (no rolling warm-up), canonicalised with a bit-reversal, then probed.
 template <int OP>
 __global__ void __launch_bounds__(CT_THREADS, 4)
 count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, int is_fastq,
                   const uint32_t* __restrict__ tile_meta, uint32_t k, KmerBucket* __restrict__ tab,
                   uint64_t cap, uint32_t cap_q, uint32_t cap_sh, unsigned long long* __restrict__ scalars) {
-  __shared__ __align__(16) uint8_t sym[CT_TILE + 2 * SYM_PAD];
+  __shared__ uint32_t s_pk[PK_WORDS];
+  __shared__ uint32_t s_nb[NB_WORDS];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
 
@@ -286,6 +326,8 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   const uint64_t owned_end = min(base + (uint64_t)CT_ADV, n);
   const uint64_t pos0 = base + (uint64_t)tid * 16;
   const uint32_t meta = tile_meta[blockIdx.x];
+  for (int i = tid; i < PK_WORDS; i += CT_THREADS) s_pk[i] = 0;
+  for (int i = tid; i < NB_WORDS; i += CT_THREADS) s_nb[i] = 0;  // (the scans below contain the barrier)
 
   // ---- 128-bit load of this thread's 16 bytes; bytes past the end read as 0 and are never emitted ----
   uint32_t w[4] = {0, 0, 0, 0};
@@ -294,7 +336,6 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     uint4 v = *reinterpret_cast<const uint4*>(text + pos0);
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   } else if (nbytes) {
-    // tail of the text: aligned words are still readable (buffers are padded / over-allocated by >= 16 B)
 #pragma unroll 1
     for (uint32_t i = 0; i < nbytes; ++i) {
       const uint32_t b = (uint32_t)(uint8_t)text[pos0 + i] << (8 * (i & 3));
@@ -313,11 +354,12 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   const uint32_t owned_bytes = pos0 >= owned_end ? 0u : (uint32_t)min((uint64_t)16, owned_end - pos0);
   const uint32_t ownedmask = owned_bytes >= 16 ? 0xffffu : ((1u << owned_bytes) - 1u);
 
-  // ---- which of my bytes are emitted as symbols (bit mask E); every emitted byte maps to codes4() ----
+  // ---- which of my bytes are emitted as symbols (bit mask E, bit i = byte i) ----
   // FASTQ: byte i is emitted iff it lies in a sequence line (line index mod 4 == 1); the newline that ends the
-  // sequence line is emitted too and becomes a reset (code 4), so k-mers never span records.
-  // FASTA: sequence-line bytes except newlines are emitted; the newline ending a HEADER line emits the reset.
-  uint32_t E = 0, force_reset = 0;  // force_reset: emitted bytes whose symbol must be 4 regardless of codes4
+  // sequence line is emitted too: it is not a base, so no k-mer spans records.
+  // FASTA: sequence-line bytes except newlines are emitted (lines of one record are joined); the newline ending a
+  // HEADER line is emitted as the record separator.
+  uint32_t E = 0;
   if (is_fastq) {
     uint32_t tot;
     uint32_t line = (meta & 3u) + block_exscan_add(__popc(nlbits), s_warp, &tot);
@@ -332,7 +374,6 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
       start = p + 1u;
       if (start > 15u) break;
     }
-    E &= bytemask;
   } else {
     const int my_last = nlbits ? tid * 16 + (31 - __clz(nlbits)) : -1;
     const int last_before = block_exscan_max(my_last, s_warp_i);  // tile-relative index or -1
@@ -350,142 +391,107 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
       const uint32_t p = rest ? (uint32_t)__ffs(rest) - 1u : 16u;  // newline ending this line piece (16: none)
       const uint32_t last = p < 16u ? p : 15u;
       const uint32_t seg = (0xffffu >> (15u - last)) & ~((1u << start) - 1u);
-      if (state == LS_SEQ) E |= seg & ~(p < 16u ? (1u << p) : 0u);       // sequence bytes, newline dropped
-      else if (p < 16u) { E |= 1u << p; force_reset |= 1u << p; }        // header: only its newline, as a reset
+      if (state == LS_SEQ) E |= seg & ~(p < 16u ? (1u << p) : 0u);  // sequence bytes, newline dropped
+      else if (p < 16u) E |= 1u << p;                                // header: only its newline (a non-base)
       if (p >= 16u) break;
       rest &= rest - 1u;
       state = LS_LINE_START;
       start = p + 1u;
     }
-    E &= bytemask;
-    force_reset &= bytemask;
   }
+  E &= bytemask;
   const uint32_t n_emit = __popc(E), n_emit_owned = __popc(E & ownedmask);
 
-  // ---- compaction into shared memory, shifted so every k-mer END lies at a compile-time offset ----
+  // ---- compaction: my emitted symbols go to positions [my_off, my_off + n_emit) of the packed stream ----
   uint32_t tot_packed;
   const uint32_t off_packed = block_exscan_add(n_emit | (n_emit_owned << 16), s_warp, &tot_packed);
-  const uint32_t my_off = off_packed & 0xffffu;
   const uint32_t n_syms = tot_packed & 0xffffu, n_owned_syms = tot_packed >> 16;
-  const uint32_t SHIFT = 33u - k;  // symbols are stored at sym[SHIFT + idx]; sym[0..SHIFT) = reset
   if (E) {
-    uint32_t sy[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sy[i] = codes4(w[i]);
-    uint8_t* dst = sym + SHIFT + my_off;
-    if (E == 0xffffu && ((SHIFT + my_off) & 3u) == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(dst)[i] = sy[i];
-    } else {
-      uint32_t rest = E;
+    uint32_t codes, notbase;
+    pack16(w, codes, notbase);
+    uint32_t pos = off_packed & 0xffffu;
+    uint32_t rest = E;
 #pragma unroll 1
-      while (rest) {
-        const uint32_t i = (uint32_t)__ffs(rest) - 1u;
-        rest &= rest - 1u;
-        *dst++ = ((force_reset >> i) & 1u) ? (uint8_t)4 : (uint8_t)byte_of(sy, i);
-      }
+    while (rest) {  // one iteration per run of consecutive emitted bytes (normally a single run)
+      const uint32_t a = (uint32_t)__ffs(rest) - 1u;
+      const uint32_t inv = ~(rest >> a);
+      const uint32_t len = inv ? (uint32_t)__ffs(inv) - 1u : 32u - a;  // <= 16
+      stream_or(s_pk, 2u * pos, (codes << (2u * a)) >> (32u - 2u * len), 2u * len);
+      const uint32_t nbv = ((notbase << (16u + a)) >> (32u - len));
+      if (nbv) stream_or(s_nb, pos, nbv, len);
+      pos += len;
+      rest &= ~(((len >= 32u ? 0u : (1u << len)) - 1u) << a);
     }
-  }
-  if ((uint32_t)tid < SHIFT) sym[tid] = 4;  // leading pad
-  if (tid < 64) {                            // trailing pad: reads reach at most n_syms + 47
-    const uint32_t p = SHIFT + n_syms + tid;
-    if (p < CT_TILE + 2 * SYM_PAD) sym[p] = 4;
   }
   __syncthreads();
 
   // halo sufficiency: an open window at the end of the look-ahead means a k-mer may have been cut
   // (only possible with pathological whitespace); report instead of silently miscounting.
   if (tid == 0 && owned_end == base + CT_ADV && n_avail > base + CT_TILE && n_syms > 0) {
-    uint32_t after = n_syms - n_owned_syms;
-    if (after < k - 1) {
+    const uint32_t after = n_syms - n_owned_syms;
+    if (after < k - 1 && n_owned_syms > 0) {
       bool open = true;
 #pragma unroll 1
-      for (uint32_t i = 0; i < after; ++i)
-        if (sym[SHIFT + n_owned_syms + i] > 3) open = false;
-      if (open && n_owned_syms > 0 && sym[SHIFT + n_owned_syms - 1] < 4) atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_HALO);
+      for (uint32_t q = n_owned_syms - 1; q < n_syms; ++q)
+        if ((s_nb[q >> 5] >> (31u - (q & 31u))) & 1u) open = false;
+      if (open) atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_HALO);
     }
   }
 
-  // ---- rolling canonical k-mers + probes: thread handles START indices [16 tid, 16 tid + 16) ----
-  // Symbols [s0, s0+32) warm the window up, every later symbol ends one k-mer (start = end - 32 in shifted
-  // coordinates).  4 k-mers per iteration: 4 independent key loads are in flight before any is resolved.
-  const uint32_t s0 = (uint32_t)tid * 16;
-  const bool active = s0 < n_owned_syms;
+  // ---- k-mers: start position p = tid + 256 i, owned by this tile iff p < n_owned_syms.  Four per round, so
+  //      8 independent 128-bit key loads are in flight per thread before any is examined. ----
   uint32_t inserted = 0, nk = 0;
-  if (__any_sync(0xffffffffu, active)) {
-    const uint32_t* sp = reinterpret_cast<const uint32_t*>(sym + s0);
-    const uint64_t mask = kmer_mask(k);
-    const uint32_t rshift = 2 * (k - 1);
-    uint64_t fwd = 0, rev = 0;
-    uint32_t run = 0;
+  const uint32_t kshift = 64u - 2u * k, vshift = 32u - k;
+  const uint64_t nbuckets = cap >> 2;
 #pragma unroll 1
-    for (int wd = 0; wd < 8; ++wd) {
-      const uint32_t xw = active ? sp[wd] : 0x04040404u;
+  for (uint32_t p0 = 0; p0 < n_owned_syms; p0 += 4 * CT_THREADS) {
+    uint64_t cn[4], bkt[4];
+    ulonglong2 ka[4], kb[4];
+    uint32_t vm = 0;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t c = (xw >> (8 * b)) & 0xff;
-        fwd = ((fwd << 2) | (c & 3u)) & mask;
-        rev = (rev >> 2) | ((uint64_t)(3u - (c & 3u)) << rshift);
-        run = c < 4 ? run + 1 : 0;
-      }
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t p = p0 + (uint32_t)i * CT_THREADS + (uint32_t)tid;
+      const uint32_t wi = p >> 4, sh = 2u * (p & 15u);
+      const uint32_t w0 = s_pk[wi], w1 = s_pk[wi + 1], w2 = s_pk[wi + 2];
+      const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+      const uint64_t fwd = (((uint64_t)hi << 32) | lo) >> kshift;
+      const uint32_t m0 = s_nb[p >> 5], m1 = s_nb[(p >> 5) + 1];
+      const uint32_t bad = __funnelshift_l(m1, m0, p & 31u) >> vshift;
+      const bool v = p < n_owned_syms && p + k <= n_syms && bad == 0;
+      const uint64_t rc = revcomp_2bit(fwd, k);
+      cn[i] = fwd < rc ? fwd : rc;
+      bkt[i] = home_slot(cn[i], cap_q, cap_sh) >> 2;
+      vm |= v ? 1u << i : 0u;
+      ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
+      kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
     }
-#pragma unroll 1
-    for (int wd = 8; wd < 12; ++wd) {
-      const uint32_t xw = active ? sp[wd] : 0x04040404u;
-      uint64_t cn[4];
-      uint32_t vm = 0;
+    nk += __popc(vm);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t c = (xw >> (8 * b)) & 0xff;
-        fwd = ((fwd << 2) | (c & 3u)) & mask;
-        rev = (rev >> 2) | ((uint64_t)(3u - (c & 3u)) << rshift);
-        run = c < 4 ? run + 1 : 0;
-        cn[b] = fwd < rev ? fwd : rev;
-        if (run >= k && s0 + (uint32_t)((wd - 8) * 4 + b) < n_owned_syms) vm |= 1u << b;
+    for (int i = 0; i < 4; ++i) {
+      const bool v = (vm >> i) & 1u;
+      const uint64_t kmer = cn[i];
+      bool hit = false;
+      uint64_t slot = 0;
+      if (v) {
+        // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
+        const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+        if (pos >= 0) {
+          hit = true;
+          slot = 4 * bkt[i] + pos;
+        } else {
+          const bool full = kb[i].y != EMPTY_KEY;  // positions fill left to right
+          if (OP == PG_OP_UPDATE) {
+            if (full) hit = resolve_lookup(kmer, bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1, slot, tab, nbuckets, scalars);
+          } else {
+            hit = resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, scalars, inserted);
+          }
+        }
       }
-      nk += __popc(vm);
-      // two k-mers per round: 2 x 4 keys (two 128-bit loads each) in flight before any is examined
-#pragma unroll
-      for (int h = 0; h < 4; h += 2) {
-        uint64_t bkt[2];
-        ulonglong2 ka[2], kb[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          bkt[i] = home_slot(cn[h + i], cap_q, cap_sh) >> 2;
-          const bool v = (vm >> (h + i)) & 1u;
-          ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
-          kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const bool v = (vm >> (h + i)) & 1u;
-          const uint64_t kmer = cn[h + i];
-          bool hit = false;
-          uint64_t slot = 0;
-          if (v) {
-            // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
-            int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
-            if (pos >= 0) {
-              hit = true;
-              slot = 4 * bkt[i] + pos;
-            } else {
-              const bool has_empty = ka[i].x == EMPTY_KEY || ka[i].y == EMPTY_KEY || kb[i].x == EMPTY_KEY || kb[i].y == EMPTY_KEY;
-              if (OP == PG_OP_UPDATE && has_empty) {
-                hit = false;
-              } else {
-                uint64_t b2 = bkt[i];
-                if (!has_empty) b2 = b2 + 1 == (cap >> 2) ? 0 : b2 + 1;  // home bucket full of other keys
-                hit = resolve_slow<OP>(kmer, b2, slot, tab, cap >> 2, scalars, inserted);
-              }
-            }
-          }
-          if (OP != PG_OP_PRIME) {
-            // warp-aggregated increment: lanes hitting the same slot elect one leader
-            const unsigned long long tag = hit ? (unsigned long long)slot : (~0ull - (unsigned)(tid & 31));
-            const unsigned peers = __match_any_sync(0xffffffffu, tag);
-            if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&tab[slot >> 2].cnt[slot & 3], (uint32_t)__popc(peers));
-          }
-        }
+      if (OP != PG_OP_PRIME) {
+        // warp-aggregated increment: lanes hitting the same slot elect one leader
+        const unsigned long long tag = hit ? (unsigned long long)slot : (~0ull - (unsigned)(tid & 31));
+        const unsigned peers = __match_any_sync(0xffffffffu, tag);
+        if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&tab[slot >> 2].cnt[slot & 3], (uint32_t)__popc(peers));
       }
     }
   }
@@ -573,9 +579,9 @@ __global__ void import_counts_kernel(KmerBucket* __restrict__ tab, uint64_t cap,
 // host side
 // ------------------------------------------------------------------------------------------------
 static int ensure_stage(pg_counter* c, bool need_host) {
-  for (int i = 0; i < 2; ++i) {
-    if (!c->d_stage[i]) PG_CUDA(cudaMalloc((void**)&c->d_stage[i], CHUNK_BYTES + 256));
-    if (need_host && !c->h_stage[i]) PG_CUDA(cudaMallocHost((void**)&c->h_stage[i], CHUNK_BYTES + 256));
+  for (int i = 0; i < pg_counter::NSTAGE; ++i) {
+    if (!c->d_stage[i]) PG_CUDA(cudaMalloc((void**)&c->d_stage[i], STAGE_BYTES + 256));
+    if (need_host && !c->h_stage[i]) PG_CUDA(cudaMallocHost((void**)&c->h_stage[i], STAGE_BYTES + 256));
   }
   return PG_OK;
 }
@@ -615,46 +621,48 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
   return PG_OK;
 }
 
-static int feed_impl(pg_counter* c, const char* src, uint64_t len, int op) {
+// Enqueues one pass over `src` (host or device text) without waiting for it: staged copies run on copy_stream ahead of
+// the kernels on c->stream.  ev0/ev1 bracket the pass on c->stream.  feed_finish() waits and checks the error flags.
+static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cudaEvent_t ev0, cudaEvent_t ev1) {
   if (!c) return fail(PG_ERR_ARG, "null counter");
   if (op < 0 || op > 2) return fail(PG_ERR_ARG, "invalid op");
-  if (len == 0) return PG_OK;
-  if (!src) return fail(PG_ERR_ARG, "null text");
-  DeviceGuard g(c->device);
+  if (!src && len) return fail(PG_ERR_ARG, "null text");
   cudaPointerAttributes attr;
   memset(&attr, 0, sizeof(attr));
-  cudaError_t pe = cudaPointerGetAttributes(&attr, src);
+  cudaError_t pe = len ? cudaPointerGetAttributes(&attr, src) : cudaSuccess;
   if (pe != cudaSuccess) {
     cudaGetLastError();
     attr.type = cudaMemoryTypeUnregistered;
   }
   const bool on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
   const bool pinned = attr.type == cudaMemoryTypeHost;
-  char first = 0;
-  if (on_device) PG_CUDA(cudaMemcpy(&first, src, 1, cudaMemcpyDeviceToHost));
-  else first = src[0];
-  int is_fastq;
-  if (first == '@') is_fastq = 1;
-  else if (first == '>') is_fastq = 0;
-  else return fail(PG_ERR_FORMAT, "unsupported sequence format: file must start with '>' (FASTA) or '@' (FASTQ)");
-
-  cudaEvent_t ev0, ev1;
-  PG_CUDA(cudaEventCreate(&ev0));
-  PG_CUDA(cudaEventCreate(&ev1));
-  // reset per-feed scalars: carry := 0 (FASTQ: header line phase; FASTA: LS_LINE_START)
-  PG_CUDA(cudaMemsetAsync(c->d_scalars + SC_CARRY, 0, sizeof(unsigned long long), c->stream));
+  int is_fastq = 0;
+  if (len) {
+    char first = 0;
+    if (on_device) PG_CUDA(cudaMemcpy(&first, src, 1, cudaMemcpyDeviceToHost));
+    else first = src[0];
+    if (first == '@') is_fastq = 1;
+    else if (first == '>') is_fastq = 0;
+    else return fail(PG_ERR_FORMAT, "unsupported sequence format: file must start with '>' (FASTA) or '@' (FASTQ)");
+  }
+  // reset per-feed scalars: carry := 0 (FASTQ: header line phase; FASTA: LS_LINE_START), k-mers of this pass := 0
+  PG_CUDA(cudaMemsetAsync(c->d_scalars + SC_CARRY, 0, 2 * sizeof(unsigned long long), c->stream));
+  static_assert(SC_KMERS == SC_CARRY + 1, "one memset clears both");
   PG_CUDA(cudaEventRecord(ev0, c->stream));
   const bool direct = on_device && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  if (!direct) PG_TRY(ensure_stage(c, !on_device && !pinned));
-  int buf = 0;
-  for (uint64_t off = 0; off < len; off += CHUNK_BYTES, buf ^= 1) {
-    const uint64_t n = std::min<uint64_t>(CHUNK_BYTES, len - off);
+  if (!direct && len) PG_TRY(ensure_stage(c, !on_device && !pinned));
+  const uint64_t step = direct ? CHUNK_BYTES : STAGE_BYTES;
+  for (uint64_t off = 0; off < len; off += step) {
+    const uint64_t n = std::min<uint64_t>(step, len - off);
     const uint64_t nh = std::min<uint64_t>(CT_HALO, len - off - n);
     const char* d_text;
+    int buf = 0;
     if (direct) {
       d_text = src + off;
     } else {
-      // wait until the kernels of two chunks ago released this staging buffer
+      buf = c->stage_next;
+      c->stage_next = (c->stage_next + 1) % pg_counter::NSTAGE;
+      // wait until the kernels that last read this staging buffer are done
       PG_CUDA(cudaEventSynchronize(c->stage_free[buf]));
       if (on_device) {
         PG_CUDA(cudaMemcpyAsync(c->d_stage[buf], src + off, n + nh, cudaMemcpyDeviceToDevice, c->copy_stream));
@@ -672,19 +680,46 @@ static int feed_impl(pg_counter* c, const char* src, uint64_t len, int op) {
     if (!direct) PG_CUDA(cudaEventRecord(c->stage_free[buf], c->stream));
   }
   PG_CUDA(cudaEventRecord(ev1, c->stream));
+  return PG_OK;
+}
+
+static int feed_finish(pg_counter* c) {
   unsigned long long sc[SC_N];
   PG_CUDA(cudaMemcpyAsync(sc, c->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
   PG_CUDA(cudaStreamSynchronize(c->stream));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ev0, ev1);
-  c->last_feed_ms = ms;
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   c->kmers_seen = sc[SC_KMERS];
   if (sc[SC_ERROR] & ERR_PROBE) return fail(PG_ERR_FULL, "k-mer table full: raise hash_size (-e)");
   if (sc[SC_ERROR] & ERR_HALO) return fail(PG_ERR_FORMAT, "sequence layout not supported: more than 97 line breaks inside one k-mer");
   if (sc[SC_DISTINCT] > c->max_distinct)
     return fail(PG_ERR_FULL, "k-mer table over its design load: " + std::to_string(sc[SC_DISTINCT]) + " distinct k-mers > " + std::to_string(c->max_distinct) + "; raise hash_size (-e)");
+  return PG_OK;
+}
+
+static int feed_impl(pg_counter* c, const char* src, uint64_t len, int op) {
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  if (len == 0) return PG_OK;
+  DeviceGuard g(c->device);
+  PG_TRY(feed_enqueue(c, src, len, op, c->ev_t0, c->ev_t1));
+  PG_TRY(feed_finish(c));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+  c->last_feed_ms = ms;
+  return PG_OK;
+}
+
+// PRIME with the segments then UPDATE with the reads (src/jellyfishcounter.cpp:61-79), enqueued back to back: the first
+// read chunks cross PCIe while the PRIME kernels still run.  Timings land in last_prime_ms / last_feed_ms.
+int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len) {
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  DeviceGuard g(c->device);
+  PG_TRY(feed_enqueue(c, segments, segments_len, PG_OP_PRIME, c->ev_p0, c->ev_p1));
+  PG_TRY(feed_enqueue(c, reads, reads_len, PG_OP_UPDATE, c->ev_t0, c->ev_t1));
+  PG_TRY(feed_finish(c));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev_p0, c->ev_p1);
+  c->last_prime_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+  c->last_feed_ms = ms;
   return PG_OK;
 }
 
@@ -744,10 +779,12 @@ extern "C" pg_counter* pg_count_new(uint32_t k, uint64_t max_distinct, int devic
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < pg_counter::NSTAGE; ++i) {
     if ((e = cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   }
+  if ((e = cudaEventCreate(&c->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&c->ev_t1)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev_p0)) != cudaSuccess || (e = cudaEventCreate(&c->ev_p1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc((void**)&c->slots, (c->capacity / 4) * sizeof(KmerBucket))) != cudaSuccess) return bail("cudaMalloc(slots)", e);
   if ((e = cudaMalloc((void**)&c->d_scalars, SC_N * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(scalars)", e);
   fill_slots_kernel<<<1184, 512, 0, c->stream>>>(c->slots, c->capacity);
@@ -765,7 +802,12 @@ extern "C" void pg_count_destroy(pg_counter* c) {
   if (c->d_counts_tmp) cudaFree(c->d_counts_tmp);
   if (c->d_scalars) cudaFree(c->d_scalars);
   if (c->d_tile_meta) cudaFree(c->d_tile_meta);
-  for (int i = 0; i < 2; ++i) {
+  if (c->d_bins) cudaFree(c->d_bins);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->ev_p0) cudaEventDestroy(c->ev_p0);
+  if (c->ev_p1) cudaEventDestroy(c->ev_p1);
+  for (int i = 0; i < pg_counter::NSTAGE; ++i) {
     if (c->d_stage[i]) cudaFree(c->d_stage[i]);
     if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -801,8 +843,7 @@ extern "C" pg_counter* pg_count_create_from_buffers(const char* reads, uint64_t 
   if (!c) return nullptr;
   int st;
   if (segments) {
-    st = feed_impl(c, segments, segments_len, PG_OP_PRIME);
-    if (st == PG_OK) st = feed_impl(c, reads, reads_len, PG_OP_UPDATE);
+    st = count_prime_update(c, segments, segments_len, reads, reads_len);
   } else {
     st = feed_impl(c, reads, reads_len, PG_OP_COUNT);
   }
@@ -905,21 +946,20 @@ extern "C" int pg_count_histogram(const pg_counter* c, uint64_t max_count, uint6
   clear_error();
   if (!c || !bins) return fail(PG_ERR_ARG, "null argument");
   DeviceGuard g(c->device);
-  unsigned long long* d_bins = nullptr;
-  PG_CUDA(cudaMalloc((void**)&d_bins, (max_count + 1) * 8));
+  pg_counter* m = const_cast<pg_counter*>(c);  // scratch only; the table is not modified
+  if (m->d_bins_cap < max_count + 1) {
+    if (m->d_bins) cudaFree(m->d_bins);
+    m->d_bins = nullptr;
+    m->d_bins_cap = 0;
+    PG_CUDA(cudaMalloc((void**)&m->d_bins, (max_count + 1) * 8));
+    m->d_bins_cap = max_count + 1;
+  }
+  unsigned long long* d_bins = m->d_bins;
   cudaMemsetAsync(d_bins, 0, (max_count + 1) * 8, c->stream);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventRecord(e0, c->stream);
   histogram_kernel<<<148 * 2, 512, 0, c->stream>>>(c->slots, c->capacity, max_count, d_bins);
   count_launch();
-  cudaEventRecord(e1, c->stream);
   cudaMemcpyAsync(bins, d_bins, (max_count + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d_bins);
   if (e != cudaSuccess) return fail(PG_ERR_CUDA, std::string("histogram: ") + cudaGetErrorString(e));
   bins[0] = 0;
   return PG_OK;
