@@ -98,6 +98,8 @@ __device__ __forceinline__ uint64_t home_slot(uint64_t kmer, uint32_t q, uint32_
   return ((uint64_t)__umulhi(hi, q) << sh) | (uint64_t)(lo & ((1u << sh) - 1u));
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 constexpr uint64_t EMPTY_KEY = ~0ULL;  // never a canonical k-mer for k <= 32 (all-T canonicalises to all-A)
 
 // The table is an array of 64-byte buckets = one DRAM burst: 4 keys (32 B, two 128-bit loads), their 4 counts

@@ -85,7 +85,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t pair_index(uint32_t a, uint32_t b) {  // VCF order (genotypingresult.cpp:61)
   const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;

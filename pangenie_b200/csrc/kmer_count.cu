@@ -254,25 +254,6 @@ __device__ __noinline__ bool resolve_insert(uint64_t kmer, uint64_t b, uint64_t&
   return false;
 }
 
-// Slow path of a lookup in a STATIC table (UPDATE): the home bucket was full of other keys; walk the following buckets
-// with one 2 x 128-bit snapshot per bucket (one latency round per bucket instead of one per key).
-__device__ __noinline__ bool resolve_lookup(uint64_t kmer, uint64_t b, uint64_t& slot, const KmerBucket* tab, uint64_t nb,
-                                            unsigned long long* scalars) {
-  for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
-    const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&tab[b].key[0]);
-    const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&tab[b].key[2]);
-    const int pos = ka.x == kmer ? 0 : ka.y == kmer ? 1 : kb.x == kmer ? 2 : kb.y == kmer ? 3 : -1;
-    if (pos >= 0) {
-      slot = 4 * b + pos;
-      return true;
-    }
-    if (kb.y == EMPTY_KEY) return false;  // positions fill left to right: an empty last position ends the search
-    b = b + 1 == nb ? 0 : b + 1;
-  }
-  atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
-  return false;
-}
-
 // ------------------------------------------------------------------------------------------------
 // pass 3: classify, pack, extract, probe
 // ------------------------------------------------------------------------------------------------
@@ -438,11 +419,22 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     }
   }
 
-  // ---- k-mers: start position p = tid + 256 i, owned by this tile iff p < n_owned_syms.  Four per round, so
-  //      8 independent 128-bit key loads are in flight per thread before any is examined. ----
+  // ---- k-mers: start position p = tid + 256 i, owned by this tile iff p < n_owned_syms. ----
   uint32_t inserted = 0, nk = 0;
   const uint32_t kshift = 64u - 2u * k, vshift = 32u - k;
   const uint64_t nbuckets = cap >> 2;
+  auto kmer_at = [&](uint32_t p, uint64_t& can) -> bool {
+    const uint32_t wi = p >> 4, sh = 2u * (p & 15u);
+    const uint32_t w0 = s_pk[wi], w1 = s_pk[wi + 1], w2 = s_pk[wi + 2];
+    const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+    const uint64_t fwd = (((uint64_t)hi << 32) | lo) >> kshift;
+    const uint32_t m0 = s_nb[p >> 5], m1 = s_nb[(p >> 5) + 1];
+    const uint32_t bad = __funnelshift_l(m1, m0, p & 31u) >> vshift;
+    const uint64_t rc = revcomp_2bit(fwd, k);
+    can = fwd < rc ? fwd : rc;
+    return p < n_owned_syms && p + k <= n_syms && bad == 0;
+  };
+  // four k-mers per round: 8 independent 128-bit key loads in flight per thread before any is examined
 #pragma unroll 1
   for (uint32_t p0 = 0; p0 < n_owned_syms; p0 += 4 * CT_THREADS) {
     uint64_t cn[4], bkt[4];
@@ -450,45 +442,75 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     uint32_t vm = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint32_t p = p0 + (uint32_t)i * CT_THREADS + (uint32_t)tid;
-      const uint32_t wi = p >> 4, sh = 2u * (p & 15u);
-      const uint32_t w0 = s_pk[wi], w1 = s_pk[wi + 1], w2 = s_pk[wi + 2];
-      const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
-      const uint64_t fwd = (((uint64_t)hi << 32) | lo) >> kshift;
-      const uint32_t m0 = s_nb[p >> 5], m1 = s_nb[(p >> 5) + 1];
-      const uint32_t bad = __funnelshift_l(m1, m0, p & 31u) >> vshift;
-      const bool v = p < n_owned_syms && p + k <= n_syms && bad == 0;
-      const uint64_t rc = revcomp_2bit(fwd, k);
-      cn[i] = fwd < rc ? fwd : rc;
+      const bool v = kmer_at(p0 + (uint32_t)i * CT_THREADS + (uint32_t)tid, cn[i]);
       bkt[i] = home_slot(cn[i], cap_q, cap_sh) >> 2;
       vm |= v ? 1u << i : 0u;
       ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
       kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
     }
     nk += __popc(vm);
+    uint32_t hitm = 0, need = 0;  // bit i: k-mer i found (slot in bkt[i]) / must look at the next bucket
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const bool v = (vm >> i) & 1u;
-      const uint64_t kmer = cn[i];
-      bool hit = false;
-      uint64_t slot = 0;
-      if (v) {
+      if ((vm >> i) & 1u) {
         // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
+        const uint64_t kmer = cn[i];
         const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+        const bool full = kb[i].y != EMPTY_KEY;  // positions fill left to right
         if (pos >= 0) {
-          hit = true;
-          slot = 4 * bkt[i] + pos;
+          hitm |= 1u << i;
+          bkt[i] = 4 * bkt[i] + pos;
+        } else if (OP == PG_OP_UPDATE) {
+          if (full) {
+            need |= 1u << i;
+            bkt[i] = bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1;
+          }
         } else {
-          const bool full = kb[i].y != EMPTY_KEY;  // positions fill left to right
-          if (OP == PG_OP_UPDATE) {
-            if (full) hit = resolve_lookup(kmer, bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1, slot, tab, nbuckets, scalars);
-          } else {
-            hit = resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, scalars, inserted);
+          uint64_t slot = 0;
+          if (resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, scalars, inserted)) {
+            hitm |= 1u << i;
+            bkt[i] = slot;
           }
         }
       }
-      if (OP != PG_OP_PRIME) {
+    }
+    if (OP == PG_OP_UPDATE) {
+      // home bucket full of other keys: walk on, again with all pending loads of the thread in flight together
+      uint32_t guard = 0;
+      while (need) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((need >> i) & 1u) {
+            ka[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]);
+            kb[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]);
+          }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((need >> i) & 1u) {
+            const uint64_t kmer = cn[i];
+            const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+            if (pos >= 0) {
+              hitm |= 1u << i;
+              need &= ~(1u << i);
+              bkt[i] = 4 * bkt[i] + pos;
+            } else if (kb[i].y == EMPTY_KEY) {
+              need &= ~(1u << i);
+            } else {
+              bkt[i] = bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1;
+            }
+          }
+        if (++guard > (1u << 20)) {
+          atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
+          break;
+        }
+      }
+    }
+    if (OP != PG_OP_PRIME) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         // warp-aggregated increment: lanes hitting the same slot elect one leader
+        const bool hit = (hitm >> i) & 1u;
+        const uint64_t slot = bkt[i];
         const unsigned long long tag = hit ? (unsigned long long)slot : (~0ull - (unsigned)(tid & 31));
         const unsigned peers = __match_any_sync(0xffffffffu, tag);
         if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&tab[slot >> 2].cnt[slot & 3], (uint32_t)__popc(peers));

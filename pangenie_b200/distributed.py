@@ -86,17 +86,25 @@ def sharded_count(counter, reads, segments, rank: int, world: int, group=None):
     `reads` is this rank's record-aligned shard (host numpy / pinned torch / cuda torch uint8); `segments` is
     only read on rank 0.  `counter` must have been created with the same max_distinct on every rank.
     """
+    import torch
     import torch.distributed as dist
     from . import PG_OP_PRIME, PG_OP_UPDATE
     slots, counts = counter_tensors(counter)
     if rank == 0:
         counter.feed(segments, PG_OP_PRIME)
+    on_gpu = slots.is_cuda
     if world > 1:
         dist.broadcast(slots, src=0, group=group)
+        if on_gpu:
+            # NCCL runs on torch's stream, the counter on its own non-blocking stream: the keys must have
+            # arrived before the UPDATE kernels probe them
+            torch.cuda.current_stream().synchronize()
     if reads is not None and len(reads):
         counter.feed(reads, PG_OP_UPDATE)
     if world > 1:
         counter.export_counts()
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        if on_gpu:
+            torch.cuda.current_stream().synchronize()  # the reduced counts must be complete before the import kernel
         counter.import_counts()
     return counter
