@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -139,8 +140,10 @@ __device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, cons
 
 struct pg_counter;
 namespace pg {
-/** PRIME (segments) + UPDATE (reads) enqueued back to back, one wait at the end (kmer_count.cu). */
-int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len);
+/** PRIME (segments) + UPDATE (reads) enqueued back to back, one wait at the end (kmer_count.cu).  `overlap`, if given,
+ *  is host work executed once the first read chunk is on its way (e.g. the panel upload of pg_genotype_run). */
+int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len,
+                       const std::function<int()>* overlap = nullptr);
 }
 
 /** Device k-mer table + streaming state (definition shared by kmer_count.cu and pipeline.cu). */
@@ -172,6 +175,10 @@ struct pg_counter {
   unsigned long long* d_bins = nullptr;  // histogram bins
   size_t d_bins_cap = 0;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // timing events of the last feed / histogram
+  // partitioned counting (kmer_count.cu): k-mer buffers of the table partitions, their cursors + the work counter
+  unsigned long long* d_part_buf = nullptr;
+  size_t part_buf_cap = 0;  // in k-mers
+  uint32_t* d_part_cursor = nullptr;  // [256]: cursors [0..255), work counter at [255]
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;  // timing events of a PRIME pass enqueued together with its UPDATE pass
   double last_prime_ms = 0.0;
 };

@@ -513,8 +513,8 @@ struct pg_engine {
   DevBuf<TJob> tjobs;
   DevBuf<ScanChrom> scan_chroms;
   DevBuf<double> scan_mats;
-  DevBuf<int32_t> scan_expo;
   DevBuf<uint32_t> seq_flags;
+  bool scan_attr_set = false;
   std::vector<uint8_t> h_is_column;
   pg_counter* cached_counter = nullptr;  // reused across pg_engine_run_resident calls
 };
@@ -569,7 +569,7 @@ extern "C" void pg_engine_destroy(pg_engine* e) {
     e->unique_kmers.release(); e->coverage_out.release(); e->col_variant.release(); e->col_cbeg.release();
     e->col_cend.release(); e->variant_col.release(); e->work_counter.release(); e->quality.release();
     e->genotype.release(); e->chroms.release(); e->jobs.release();
-    e->tjobs.release(); e->scan_chroms.release(); e->scan_mats.release(); e->scan_expo.release(); e->seq_flags.release();
+    e->tjobs.release(); e->scan_chroms.release(); e->scan_mats.release(); e->seq_flags.release();
   }
   delete e;
 }
@@ -882,6 +882,8 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
         const ChromCols& ch = chroms[c];
         sch[c].n_tj = ch.n_blocks > 1 ? ch.n_blocks - 1 : 0;
         sch[c].pad = 0;
+        sch[c].out_first[0] = ch.blk_begin + 1;                              // forward job k writes slot blk_begin + k + 1
+        sch[c].out_first[1] = ch.blk_begin + (ch.n_blocks > 1 ? ch.n_blocks - 2 : 0);  // backward: k = n_blocks-1 first -> slot k - 1
         sch[c].tj_begin[0] = (uint32_t)tj.size();
         for (uint32_t k = 0; k + 1 < ch.n_blocks; ++k) {  // forward: block k -> F at its last column
           TJob j;
@@ -910,17 +912,16 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
       sp.n_tj = (uint32_t)tj.size();
       sp.n_groups = (NB + G - 1) / G;
       sp.n_items = sp.n_tj * sp.n_groups;
-      sp.mat_stride = (NB * NB + 1u) & ~1u;
+      sp.mat_stride = ((NB + 1u) * NB + 1u) & ~1u;
       PG_TRY(e->tjobs.reserve(tj.size()));
       PG_TRY(e->scan_chroms.reserve(e->n_chrom));
       PG_TRY(e->scan_mats.reserve((size_t)sp.n_tj * sp.mat_stride));
-      PG_TRY(e->scan_expo.reserve((size_t)sp.n_tj * NB));
       PG_TRY(e->seq_flags.reserve(e->n_chrom));
       PG_CUDA(cudaMemcpyAsync(e->tjobs.p, tj.data(), tj.size() * sizeof(TJob), cudaMemcpyHostToDevice, s));
       PG_CUDA(cudaMemcpyAsync(e->scan_chroms.p, sch.data(), sch.size() * sizeof(ScanChrom), cudaMemcpyHostToDevice, s));
       PG_CUDA(cudaMemsetAsync(e->seq_flags.p, 0, e->n_chrom * sizeof(uint32_t), s));
       PG_CUDA(cudaStreamSynchronize(s));  // tj / sch are stack-owned host vectors
-      sp.tjobs = e->tjobs.p; sp.mats = e->scan_mats.p; sp.expo = e->scan_expo.p; sp.chroms = e->scan_chroms.p;
+      sp.tjobs = e->tjobs.p; sp.mats = e->scan_mats.p; sp.chroms = e->scan_chroms.p;
       sp.seq_flags = e->seq_flags.p;
       cp.seq_flags = e->seq_flags.p;
     }
@@ -956,7 +957,11 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     }
     if (use_scan) {
       basis_kernel<SCAN_CPL><<<(sp.n_items + BASIS_WARPS - 1) / BASIS_WARPS, BASIS_WARPS * 32, 0, s>>>(cp, sp);
-      scan_kernel<SCAN_CPL><<<dim3(e->n_chrom, 2), SCAN_THREADS, 0, s>>>(cp, sp);
+      if (!e->scan_attr_set) {  // per device: the engine owns one device
+        PG_CUDA(cudaFuncSetAttribute(scan_kernel<SCAN_CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem<SCAN_CPL>)));
+        e->scan_attr_set = true;
+      }
+      scan_kernel<SCAN_CPL><<<dim3(e->n_chrom, 2), SCAN_THREADS, sizeof(ScanSmem<SCAN_CPL>), s>>>(cp, sp);
       count_launch(2);
       PG_CUDA(cudaGetLastError());
       scan_used = 1;
@@ -1144,8 +1149,15 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   }
   tr.mark("clear");
   pg_counter* c = e->cached_counter;
+  bool panels_loaded = false;
   if (in->segments) {
-    PG_TRY(count_prime_update(c, in->segments, in->segments_len, in->reads, in->reads_len));
+    // the panel upload (host-side flattening + 12 small copies) runs while the first read chunks cross PCIe
+    const std::function<int()> upload = [&]() -> int {
+      PG_TRY(engine_load_panels(e, n_chrom, panels, results, false, true));
+      panels_loaded = true;
+      return PG_OK;
+    };
+    PG_TRY(count_prime_update(c, in->segments, in->segments_len, in->reads, in->reads_len, &upload));
     e->tm.prime_ms = c->last_prime_ms;
   } else {
     PG_TRY(pg_count_feed(c, in->reads, in->reads_len, PG_OP_COUNT));
@@ -1167,7 +1179,7 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   } tguard{&table};
   tr.mark("histogram+table");
   // 4) fill + 5) HMM, panel uploaded once
-  PG_TRY(engine_load_panels(e, n_chrom, panels, results, false, true));
+  if (!panels_loaded) PG_TRY(engine_load_panels(e, n_chrom, panels, results, false, true));
   tr.mark("load_panels");
   PG_TRY(engine_fill(e, c, peak));
   tr.mark("fill");

@@ -39,6 +39,7 @@ struct TJob {
 struct ScanChrom {
   uint32_t tj_begin[2];  // first transfer job of the forward / backward chain (processing order)
   uint32_t n_tj;         // jobs per direction (= n_blocks - 1, 0 if the chromosome has a single block)
+  uint32_t out_first[2]; // checkpoint slot written by the first job of each chain; forward counts up, backward down
   uint32_t pad;
 };
 
@@ -47,9 +48,9 @@ struct ScanParams {
   uint32_t n_tj;
   uint32_t n_groups;     // basis groups per job = ceil(NB / chains per warp)
   uint32_t n_items;      // n_tj * n_groups
-  uint32_t mat_stride;   // doubles per transfer matrix (NB*NB rounded up to even)
-  double* mats;          // [n_tj][mat_stride]: row b = image of basis element b, upper-triangle cell order
-  int32_t* expo;         // [n_tj][NB] power-of-two exponent of each row
+  uint32_t mat_stride;   // doubles per transfer matrix ((NB+1)*NB rounded up to even)
+  double* mats;          // [n_tj][mat_stride]: row b < NB = image of basis element b (upper-triangle cell order),
+                         // row NB = power-of-two exponent of each row (as doubles, so one cp.async stream brings both)
   const ScanChrom* chroms;
   uint32_t* seq_flags;   // [n_chrom] != 0 -> sequential recomputation required
 };
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(BASIS_WARPS * 32) basis_kernel(const ChainPara
 #pragma unroll
     for (int s = 0; s < CPL; ++s)
       if (s >= r && s < P) out[tri_index(r, s, P)] = x[s];
-    if (r == 0) sp.expo[(size_t)tj * NB + b] = E;
+    if (r == 0) sp.mats[(size_t)tj * sp.mat_stride + (size_t)NB * NB + b] = (double)E;  // row NB: the exponents
   }
   if (chain_ok && dead) atomicOr(sp.seq_flags + job.chrom, 1u);
 }
@@ -181,15 +182,22 @@ __global__ void __launch_bounds__(BASIS_WARPS * 32) basis_kernel(const ChainPara
 // 2. checkpoint scan.  grid = (n_chrom, 2): y = 0 forward, y = 1 backward; one upper-triangle cell per thread.
 //    Checkpoints are written in the thread-major layout of Chain<1, CPL, 1, 32> (cell (i,j) at [j*32 + i]).
 // -------------------------------------------------------------------------------------------------
+constexpr int SCAN_RING = 4;  // transfer matrices in flight (L2 -> shared memory), one cp.async group each
+template <int CPL>
+struct ScanSmem {
+  static constexpr int NBMAX = CPL * (CPL + 1) / 2;
+  static constexpr int MATMAX = ((NBMAX + 1) * NBMAX + 1) & ~1;
+  double mat[SCAN_RING][MATMAX];
+  double st[NBMAX];  // current state, upper triangle
+  double w[NBMAX];
+  double tot[2];
+  int key[2];
+};
+
 template <int CPL>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p, const ScanParams sp) {
-  constexpr int NBMAX = CPL * (CPL + 1) / 2;
-  constexpr int MATMAX = (NBMAX * NBMAX + 1) & ~1;
-  __shared__ __align__(16) double mat[2][MATMAX];
-  __shared__ double st[NBMAX];   // current state, upper triangle
-  __shared__ double w[NBMAX];
-  __shared__ int s_key[2];
-  __shared__ double s_tot[2];
+  extern __shared__ __align__(16) unsigned char scan_smem_raw[];
+  ScanSmem<CPL>& sm = *reinterpret_cast<ScanSmem<CPL>*>(scan_smem_raw);
   const uint32_t chrom = blockIdx.x, dir = blockIdx.y;
   const ScanChrom sc = sp.chroms[chrom];
   if (sc.n_tj == 0) return;
@@ -200,14 +208,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
   const uint32_t tj0 = sc.tj_begin[dir];
   const uint32_t chunks = sp.mat_stride / 2;  // 16-byte pieces per matrix
 
-  auto prefetch = [&](uint32_t q, int bufi) {
+  // the matrices do not depend on the chain: they stream in SCAN_RING - 1 steps ahead of their use
+  auto prefetch = [&](uint32_t q) {
     if (q < sc.n_tj) {
       const double* src = sp.mats + (size_t)(tj0 + q) * sp.mat_stride;
-      for (uint32_t c = tid; c < chunks; c += SCAN_THREADS) cp_async16(&mat[bufi][2 * c], src + 2 * c);
+      double* dst = sm.mat[q % SCAN_RING];
+      for (uint32_t c = tid; c < chunks; c += SCAN_THREADS) cp_async16(dst + 2 * c, src + 2 * c);
     }
     cp_async_commit();
   };
-  prefetch(0, 0);
+  for (uint32_t q = 0; q + 1 < SCAN_RING; ++q) prefetch(q);
 
   // my cell (ci <= cj)
   int ci = 0, cj = 0;
@@ -226,58 +236,57 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
     const double* d = reinterpret_cast<const double*>(p.desc + (size_t)(uint32_t)t * p.desc_stride);
     ColEm em;
     em.load(d, ci, cell_ok);
-    if (cell_ok) st[tid] = em.at(cj, true);
+    if (cell_ok) sm.st[tid] = em.at(cj, true);
   }
   __syncthreads();
 
   for (uint32_t q = 0; q < sc.n_tj; ++q) {
-    const int cur = (int)(q & 1u);
-    prefetch(q + 1, cur ^ 1);
-    const uint32_t tj = tj0 + q;
+    prefetch(q + SCAN_RING - 1);  // its ring slot was last read in step q - 1 (barrier at the end of that step)
+    cp_async_wait<SCAN_RING - 1>();  // all but the newest SCAN_RING - 1 groups are complete: matrix q has landed
+    __syncthreads();
     // ---- weights: coefficient of basis b = state cell b, times the row's power-of-two scale, relative to the largest
     double coef = 0.0;
     int key = INT_MIN, Eb = 0;
     if (cell_ok) {
-      coef = st[tid];
-      Eb = sp.expo[(size_t)tj * NB + tid];
+      coef = sm.st[tid];
+      Eb = (int)sm.mat[q % SCAN_RING][NB * NB + tid];
       if (coef > 0.0) key = (((__double2hiint(coef) >> 20) & 0x7ff) - 1023) + Eb;
     }
     int kmax = key;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    if (lane == 0) s_key[wid] = kmax;
+    if (lane == 0) sm.key[wid] = kmax;
     __syncthreads();
-    kmax = max(s_key[0], s_key[1]);
+    kmax = max(sm.key[0], sm.key[1]);
     if (cell_ok) {
       double wv = 0.0;
       if (coef > 0.0) {
         const int sh = Eb - kmax;  // <= 0 up to the coefficient's own exponent
         wv = sh < -2000 ? 0.0 : scalbn(coef, sh);
       }
-      w[tid] = wv;
+      sm.w[tid] = wv;
     }
-    cp_async_wait<1>();
     __syncthreads();
     // ---- new cell value
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (cell_ok) {
-      const double* m = &mat[cur][tid];
+      const double* m = &sm.mat[q % SCAN_RING][tid];
       int b = 0;
       for (; b + 3 < NB; b += 4) {
-        a0 = fma(w[b], m[(size_t)b * NB], a0);
-        a1 = fma(w[b + 1], m[(size_t)(b + 1) * NB], a1);
-        a2 = fma(w[b + 2], m[(size_t)(b + 2) * NB], a2);
-        a3 = fma(w[b + 3], m[(size_t)(b + 3) * NB], a3);
+        a0 = fma(sm.w[b], m[(size_t)b * NB], a0);
+        a1 = fma(sm.w[b + 1], m[(size_t)(b + 1) * NB], a1);
+        a2 = fma(sm.w[b + 2], m[(size_t)(b + 2) * NB], a2);
+        a3 = fma(sm.w[b + 3], m[(size_t)(b + 3) * NB], a3);
       }
-      for (; b < NB; ++b) a0 = fma(w[b], m[(size_t)b * NB], a0);
+      for (; b < NB; ++b) a0 = fma(sm.w[b], m[(size_t)b * NB], a0);
     }
     double v = (a0 + a1) + (a2 + a3);
     double tot = cell_ok ? (ci == cj ? v : 2.0 * v) : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) s_tot[wid] = tot;
-    __syncthreads();  // also: everyone is done reading st[] / w[] / mat[cur]
-    const double T = s_tot[0] + s_tot[1];
+    if (lane == 0) sm.tot[wid] = tot;
+    __syncthreads();  // also: everyone is done reading st[] / w[] / the matrix
+    const double T = sm.tot[0] + sm.tot[1];
     if (!(T > 0.0)) {  // dead checkpoint: the uniform replacement is not linear -> sequential recomputation
       if (tid == 0) atomicOr(sp.seq_flags + chrom, 1u);
       cp_async_wait<0>();
@@ -285,8 +294,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
     }
     v *= pow2_scale_of(T);
     if (cell_ok) {
-      st[tid] = v;
-      double* out = (dir ? p.ckpt_bwd : p.ckpt_fwd) + (size_t)sp.tjobs[tj].out_blk * p.state_stride;
+      sm.st[tid] = v;
+      const uint32_t out_blk = dir ? sc.out_first[1] - q : sc.out_first[0] + q;
+      double* out = (dir ? p.ckpt_bwd : p.ckpt_fwd) + (size_t)out_blk * p.state_stride;
       out[(size_t)cj * 32 + ci] = v;
       if (ci != cj) out[(size_t)ci * 32 + cj] = v;
     }

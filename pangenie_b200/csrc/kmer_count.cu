@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -285,6 +286,182 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], uint32_t i) 
   return (x >> (8 * (i & 3))) & 0xff;
 }
 
+struct TableRef {
+  KmerBucket* tab;
+  uint64_t nbuckets;
+  uint32_t cap_q, cap_sh;
+  unsigned long long* scalars;
+  uint32_t flags;  // bit 0: plain atomics instead of warp-aggregated ones (experiment knob PG_COUNT_NOAGG)
+};
+
+// Lookups whose home bucket is full of other keys (~8% at load 0.6) continue in the next bucket.  Doing that inside the
+// batched probe makes every warp execute the walk for a handful of lanes; instead they are parked in a shared-memory
+// queue and worked off afterwards with all lanes busy (drain_walks).
+constexpr uint32_t WQ_CAP = 768;
+struct WalkQueue {
+  uint32_t n;
+  uint32_t pad;
+  unsigned long long kmer[WQ_CAP];
+  unsigned long long bkt[WQ_CAP];
+};
+
+// walks from bucket b in a STATIC table; counts the k-mer if present
+__device__ __noinline__ void walk_count(uint64_t kmer, uint64_t b, const TableRef& T) {
+  for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
+    const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&T.tab[b].key[0]);
+    const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&T.tab[b].key[2]);
+    const int pos = ka.x == kmer ? 0 : ka.y == kmer ? 1 : kb.x == kmer ? 2 : kb.y == kmer ? 3 : -1;
+    if (pos >= 0) {
+      atomicAdd(&T.tab[b].cnt[pos], 1u);
+      return;
+    }
+    if (kb.y == EMPTY_KEY) return;  // positions fill left to right: an empty last position ends the search
+    b = b + 1 == T.nbuckets ? 0 : b + 1;
+  }
+  atomicOr(T.scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
+}
+
+// block-wide: resolves the parked lookups, one per thread.  Contains barriers: call from uniform control flow.
+__device__ __forceinline__ void drain_walks(WalkQueue* wq, const TableRef& T) {
+  __syncthreads();
+  const uint32_t n = min(wq->n, WQ_CAP);
+  for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) walk_count(wq->kmer[j], wq->bkt[j], T);
+  __syncthreads();
+  if (threadIdx.x == 0) wq->n = 0;
+  __syncthreads();
+}
+
+// Looks up / inserts (OP) the canonical k-mers cn[i], i in vm, and counts the hits.  Must be called by all 32 lanes
+// of a warp (warp-aggregated increments).  Eight independent 128-bit key loads are in flight per thread before any
+// is examined.  UPDATE: unresolved lookups are parked in `wq` (the caller drains it).
+template <int OP, bool USEQ>
+__device__ __forceinline__ void probe4(const uint64_t (&cn)[4], uint32_t vm, const TableRef& T, uint32_t& inserted, WalkQueue* wq) {
+  uint64_t bkt[4];
+  ulonglong2 ka[4], kb[4];
+  KmerBucket* tab = T.tab;
+  const uint64_t nbuckets = T.nbuckets;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool v = (vm >> i) & 1u;
+    bkt[i] = home_slot(cn[i], T.cap_q, T.cap_sh) >> 2;
+    ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
+    kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
+  }
+  uint32_t hitm = 0, need = 0;  // bit i: k-mer i found, its slot is in bkt[i] / continue in bucket bkt[i]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if ((vm >> i) & 1u) {
+      // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
+      const uint64_t kmer = cn[i];
+      const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+      const bool full = kb[i].y != EMPTY_KEY;  // positions fill left to right
+      if (pos >= 0) {
+        hitm |= 1u << i;
+        bkt[i] = 4 * bkt[i] + pos;
+      } else if (OP == PG_OP_UPDATE) {
+        if (full) {
+          const uint64_t nxt = bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1;
+          if (USEQ) {
+            const uint32_t q = atomicAdd(&wq->n, 1u);
+            if (q < WQ_CAP) {
+              wq->kmer[q] = kmer;
+              wq->bkt[q] = nxt;
+            } else {
+              walk_count(kmer, nxt, T);  // queue full (pathological collision chains): resolve in place
+            }
+          } else {
+            need |= 1u << i;
+            bkt[i] = nxt;
+          }
+        }
+      } else {
+        uint64_t slot = 0;
+        if (resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, T.scalars, inserted)) {
+          hitm |= 1u << i;
+          bkt[i] = slot;
+        }
+      }
+    }
+  }
+  if (OP == PG_OP_UPDATE && !USEQ) {
+    // walk on in place, again with all pending loads of the thread in flight together
+    uint32_t guard = 0;
+    while (need) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if ((need >> i) & 1u) {
+          ka[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]);
+          kb[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if ((need >> i) & 1u) {
+          const uint64_t kmer = cn[i];
+          const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+          if (pos >= 0) {
+            hitm |= 1u << i;
+            need &= ~(1u << i);
+            bkt[i] = 4 * bkt[i] + pos;
+          } else if (kb[i].y == EMPTY_KEY) {
+            need &= ~(1u << i);
+          } else {
+            bkt[i] = bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1;
+          }
+        }
+      if (++guard > (1u << 20)) {
+        atomicOr(T.scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
+        break;
+      }
+    }
+  }
+  if (OP != PG_OP_PRIME && (T.flags & 1u)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if ((hitm >> i) & 1u) atomicAdd(&tab[bkt[i] >> 2].cnt[bkt[i] & 3], 1u);
+  } else if (OP != PG_OP_PRIME) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // warp-aggregated increment: lanes hitting the same slot elect one leader
+      const bool hit = (hitm >> i) & 1u;
+      const uint64_t slot = bkt[i];
+      const unsigned long long tag = hit ? (unsigned long long)slot : (~0ull - lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, tag);
+      if (hit && (__ffs(peers) - 1) == (int)lane) atomicAdd(&tab[slot >> 2].cnt[slot & 3], (uint32_t)__popc(peers));
+    }
+  }
+}
+
+// One k-mer, no warp cooperation (divergent callers: partition-region overflow).
+template <int OP>
+__device__ __noinline__ void probe1(uint64_t kmer, const TableRef& T, uint32_t& inserted) {
+  uint64_t b = home_slot(kmer, T.cap_q, T.cap_sh) >> 2;
+  if (OP != PG_OP_UPDATE) {
+    uint64_t slot = 0;
+    if (resolve_insert<OP>(kmer, b, slot, T.tab, T.nbuckets, T.scalars, inserted) && OP != PG_OP_PRIME)
+      atomicAdd(&T.tab[slot >> 2].cnt[slot & 3], 1u);
+    return;
+  }
+  walk_count(kmer, b, T);
+}
+
+// ---- partitioned counting -------------------------------------------------------------------------------------
+// A table much larger than the L2 makes every probe a random DRAM burst (64 B read + 32 B write-back for an 8-byte
+// key and a 4-byte count).  With partitioning the tile kernel does not probe: it appends each canonical k-mer to the
+// buffer of the table partition its home bucket lies in (streaming 8-byte writes), and probe_parts_kernel then works
+// through the partitions one after the other, so the slice of the table being hit (<= ~24 MB) stays L2-resident.
+constexpr int MAX_PARTS = 255;
+struct PartArgs {
+  uint64_t* buf;         // [n_parts][region_cap] canonical k-mers
+  uint32_t* cursor;      // [n_parts] k-mers appended (may run past region_cap: the excess was probed directly)
+  uint32_t* work;        // probe_parts_kernel work-item counter
+  uint32_t region_cap;
+  uint32_t n_parts;
+};
+__device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
+  return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
+}
+
 constexpr int PK_WORDS = CT_TILE / 16 + 4;  // packed codes: 16 symbols per word (+ read-ahead padding)
 constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per word
 
@@ -292,15 +469,19 @@ constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per 
 // into a 2-bit packed stream in shared memory, and k-mer START positions are dealt to the threads round-robin, so all
 // lanes stay busy whatever fraction of the text is sequence (FASTQ: ~48%).  A k-mer is one funnel-shift extraction from
 // the packed stream (no rolling warm-up), canonicalised with a bit-reversal, then probed.
-template <int OP>
+template <int OP, bool SCATTER>
 __global__ void __launch_bounds__(CT_THREADS, 4)
 count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, int is_fastq,
-                  const uint32_t* __restrict__ tile_meta, uint32_t k, KmerBucket* __restrict__ tab,
-                  uint64_t cap, uint32_t cap_q, uint32_t cap_sh, unsigned long long* __restrict__ scalars) {
+                  const uint32_t* __restrict__ tile_meta, uint32_t k, const TableRef T, const PartArgs pa) {
   __shared__ uint32_t s_pk[PK_WORDS];
   __shared__ uint32_t s_nb[NB_WORDS];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
+  __shared__ uint32_t s_cnt[SCATTER ? MAX_PARTS + 1 : 1];   // k-mers of this tile per partition, then write cursors
+  __shared__ uint8_t s_part[SCATTER ? CT_TILE : 1];         // partition of the k-mer starting at each symbol (255: none)
+  unsigned long long* scalars = T.scalars;
+  if (SCATTER)
+    for (int i = threadIdx.x; i <= MAX_PARTS; i += CT_THREADS) s_cnt[i] = 0;
 
   const int tid = threadIdx.x;
   const uint64_t base = (uint64_t)blockIdx.x * CT_ADV;
@@ -422,7 +603,6 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   // ---- k-mers: start position p = tid + 256 i, owned by this tile iff p < n_owned_syms. ----
   uint32_t inserted = 0, nk = 0;
   const uint32_t kshift = 64u - 2u * k, vshift = 32u - k;
-  const uint64_t nbuckets = cap >> 2;
   auto kmer_at = [&](uint32_t p, uint64_t& can) -> bool {
     const uint32_t wi = p >> 4, sh = 2u * (p & 15u);
     const uint32_t w0 = s_pk[wi], w1 = s_pk[wi + 1], w2 = s_pk[wi + 2];
@@ -434,86 +614,46 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     can = fwd < rc ? fwd : rc;
     return p < n_owned_syms && p + k <= n_syms && bad == 0;
   };
-  // four k-mers per round: 8 independent 128-bit key loads in flight per thread before any is examined
+  if (!SCATTER) {
+    // four k-mers per round
 #pragma unroll 1
-  for (uint32_t p0 = 0; p0 < n_owned_syms; p0 += 4 * CT_THREADS) {
-    uint64_t cn[4], bkt[4];
-    ulonglong2 ka[4], kb[4];
-    uint32_t vm = 0;
+    for (uint32_t p0 = 0; p0 < n_owned_syms; p0 += 4 * CT_THREADS) {
+      uint64_t cn[4];
+      uint32_t vm = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool v = kmer_at(p0 + (uint32_t)i * CT_THREADS + (uint32_t)tid, cn[i]);
-      bkt[i] = home_slot(cn[i], cap_q, cap_sh) >> 2;
-      vm |= v ? 1u << i : 0u;
-      ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
-      kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
+      for (int i = 0; i < 4; ++i) vm |= kmer_at(p0 + (uint32_t)i * CT_THREADS + (uint32_t)tid, cn[i]) ? 1u << i : 0u;
+      nk += __popc(vm);
+      probe4<OP, false>(cn, vm, T, inserted, nullptr);
     }
-    nk += __popc(vm);
-    uint32_t hitm = 0, need = 0;  // bit i: k-mer i found (slot in bkt[i]) / must look at the next bucket
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if ((vm >> i) & 1u) {
-        // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
-        const uint64_t kmer = cn[i];
-        const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
-        const bool full = kb[i].y != EMPTY_KEY;  // positions fill left to right
-        if (pos >= 0) {
-          hitm |= 1u << i;
-          bkt[i] = 4 * bkt[i] + pos;
-        } else if (OP == PG_OP_UPDATE) {
-          if (full) {
-            need |= 1u << i;
-            bkt[i] = bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1;
-          }
-        } else {
-          uint64_t slot = 0;
-          if (resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, scalars, inserted)) {
-            hitm |= 1u << i;
-            bkt[i] = slot;
-          }
-        }
+  } else {
+    // (1) count my k-mers per partition, (2) reserve one contiguous range per partition for the whole tile,
+    // (3) append.  A partition region that is full (skewed data) sends its k-mers straight to the table.
+#pragma unroll 1
+    for (uint32_t p = (uint32_t)tid; p < n_owned_syms; p += CT_THREADS) {
+      uint64_t can;
+      uint32_t part = 255u;
+      if (kmer_at(p, can)) {
+        part = part_of(can, pa.n_parts);
+        atomicAdd(&s_cnt[part], 1u);
+        ++nk;
       }
+      s_part[p] = (uint8_t)part;
     }
-    if (OP == PG_OP_UPDATE) {
-      // home bucket full of other keys: walk on, again with all pending loads of the thread in flight together
-      uint32_t guard = 0;
-      while (need) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if ((need >> i) & 1u) {
-            ka[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]);
-            kb[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]);
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if ((need >> i) & 1u) {
-            const uint64_t kmer = cn[i];
-            const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
-            if (pos >= 0) {
-              hitm |= 1u << i;
-              need &= ~(1u << i);
-              bkt[i] = 4 * bkt[i] + pos;
-            } else if (kb[i].y == EMPTY_KEY) {
-              need &= ~(1u << i);
-            } else {
-              bkt[i] = bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1;
-            }
-          }
-        if (++guard > (1u << 20)) {
-          atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
-          break;
-        }
-      }
+    __syncthreads();
+    for (uint32_t q = (uint32_t)tid; q < pa.n_parts; q += CT_THREADS) {
+      const uint32_t cnt = s_cnt[q];
+      s_cnt[q] = cnt ? atomicAdd(pa.cursor + q, cnt) : 0u;
     }
-    if (OP != PG_OP_PRIME) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // warp-aggregated increment: lanes hitting the same slot elect one leader
-        const bool hit = (hitm >> i) & 1u;
-        const uint64_t slot = bkt[i];
-        const unsigned long long tag = hit ? (unsigned long long)slot : (~0ull - (unsigned)(tid & 31));
-        const unsigned peers = __match_any_sync(0xffffffffu, tag);
-        if (hit && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&tab[slot >> 2].cnt[slot & 3], (uint32_t)__popc(peers));
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t p = (uint32_t)tid; p < n_owned_syms; p += CT_THREADS) {
+      const uint32_t part = s_part[p];
+      if (part != 255u) {
+        uint64_t can;
+        kmer_at(p, can);
+        const uint32_t pos = atomicAdd(&s_cnt[part], 1u);
+        if (pos < pa.region_cap) pa.buf[(size_t)part * pa.region_cap + pos] = can;
+        else probe1<OP>(can, T, inserted);
       }
     }
   }
@@ -526,6 +666,59 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     if (inserted) atomicAdd(scalars + SC_DISTINCT, (unsigned long long)inserted);
     if (nk) atomicAdd(scalars + SC_KMERS, (unsigned long long)nk);
   }
+}
+
+// Works through the partition buffers in partition order (persistent CTAs pulling items of PP_ITEM k-mers), so the
+// CTAs running at any moment hit one or two adjacent slices of the table.
+constexpr int PP_ITEM = 4096;
+template <int OP>
+__global__ void __launch_bounds__(256, 3) probe_parts_kernel(const PartArgs pa, const TableRef T) {
+  __shared__ uint32_t s_start[MAX_PARTS + 2];  // first item of each partition
+  __shared__ WalkQueue s_wq;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (uint32_t q = 0; q < pa.n_parts; ++q) {
+      s_start[q] = run;
+      const uint32_t nq = min(pa.cursor[q], pa.region_cap);
+      run += (nq + PP_ITEM - 1) / PP_ITEM;
+    }
+    s_start[pa.n_parts] = run;
+    s_wq.n = 0;
+  }
+  __syncthreads();
+  const uint32_t total = s_start[pa.n_parts];
+  uint32_t inserted = 0;
+  // items are dealt round-robin: the CTAs running at any moment work on neighbouring items = the same table slice
+  for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+    uint32_t lo = 0, hi = pa.n_parts;  // largest q with s_start[q] <= item
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_start[mid] <= item) lo = mid;
+      else hi = mid;
+    }
+    const uint32_t q = lo;
+    const uint32_t nq = min(pa.cursor[q], pa.region_cap);
+    const uint32_t off = (item - s_start[q]) * PP_ITEM;
+    const uint64_t* src = pa.buf + (size_t)q * pa.region_cap + off;
+    const uint32_t m = min((uint32_t)PP_ITEM, nq - off);
+#pragma unroll 1
+    for (uint32_t r = 0; r < m; r += 4 * 256) {
+      uint64_t cn[4];
+      uint32_t vm = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t j = r + (uint32_t)i * 256 + (uint32_t)tid;
+        const bool v = j < m;
+        cn[i] = v ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
+        vm |= v ? 1u << i : 0u;
+      }
+      probe4<OP, true>(cn, vm, T, inserted, &s_wq);
+    }
+    if (OP == PG_OP_UPDATE) drain_walks(&s_wq, T);
+  }
+  for (int o = 16; o > 0; o >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
+  if ((tid & 31) == 0 && inserted) atomicAdd(T.scalars + SC_DISTINCT, (unsigned long long)inserted);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -619,7 +812,23 @@ static int ensure_tile_meta(pg_counter* c, size_t n_tiles) {
   return PG_OK;
 }
 
-static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t n_avail, int is_fastq, int op) {
+static uint64_t env_u64(const char* name, uint64_t dflt) {
+  const char* e = getenv(name);
+  return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : dflt;
+}
+static TableRef table_ref(const pg_counter* c) {
+  TableRef T;
+  T.tab = c->slots;
+  T.nbuckets = c->capacity >> 2;
+  T.cap_q = c->cap_q;
+  T.cap_sh = c->cap_sh;
+  T.scalars = c->d_scalars;
+  T.flags = env_u64("PG_COUNT_NOAGG", 0) ? 1u : 0u;
+  return T;
+}
+
+// `pa` non-null: scatter the k-mers of this chunk into the partition buffers instead of probing the table
+static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t n_avail, int is_fastq, int op, const PartArgs* pa) {
   const uint32_t n_tiles = (uint32_t)((n + CT_ADV - 1) / CT_ADV);
   if (n_tiles == 0) return PG_OK;
   PG_TRY(ensure_tile_meta(c, n_tiles));
@@ -628,24 +837,77 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
   int64_t* lnl = reinterpret_cast<int64_t*>(meta + 2 * c->tile_meta_cap);
   tile_lines_kernel<<<n_tiles, 256, 0, c->stream>>>(d_text, n, nlc, lnl);
   tile_scan_kernel<<<1, 1024, 0, c->stream>>>(d_text, n, n_tiles, nlc, lnl, is_fastq, meta, c->d_scalars);
-  switch (op) {
-    case PG_OP_COUNT:
-      count_tile_kernel<PG_OP_COUNT><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
-      break;
-    case PG_OP_PRIME:
-      count_tile_kernel<PG_OP_PRIME><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
-      break;
-    default:
-      count_tile_kernel<PG_OP_UPDATE><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, c->slots, c->capacity, c->cap_q, c->cap_sh, c->d_scalars);
+  const TableRef T = table_ref(c);
+  PartArgs none;
+  memset(&none, 0, sizeof(none));
+  if (pa) {
+    if (op == PG_OP_COUNT) count_tile_kernel<PG_OP_COUNT, true><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
+    else count_tile_kernel<PG_OP_UPDATE, true><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
+  } else {
+    switch (op) {
+      case PG_OP_COUNT: count_tile_kernel<PG_OP_COUNT, false><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, none); break;
+      case PG_OP_PRIME: count_tile_kernel<PG_OP_PRIME, false><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, none); break;
+      default: count_tile_kernel<PG_OP_UPDATE, false><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, none);
+    }
   }
   count_launch(3);
   PG_CUDA(cudaGetLastError());
   return PG_OK;
 }
 
+// ---- partitioned counting: geometry and the probe pass over the filled buffers ----
+constexpr uint64_t SUPER_BYTES = 1ull << 30;  // text bytes scattered before the partition buffers are worked off
+// tuning / test knobs: PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
+// PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning
+static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 96u << 10) << 10; }
+
+// decides whether this pass is partitioned; sizes the buffers for a super-chunk of `super` text bytes
+static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, PartArgs& pa, bool& use) {
+  use = false;
+  // text streamed over PCIe arrives slower than the direct kernel counts it: partitioning would only add a tail
+  if (!resident && !env_u64("PG_COUNT_PART_STAGED", 0)) return PG_OK;
+  const uint64_t slice = part_slice_bytes();
+  const uint64_t table_bytes = (c->capacity >> 2) * sizeof(KmerBucket);
+  if (op == PG_OP_PRIME || slice == 0 || table_bytes <= 2 * slice || len < env_u64("PG_COUNT_PART_MIN_TEXT", 4u << 20)) return PG_OK;
+  const uint32_t n_parts = (uint32_t)std::min<uint64_t>(MAX_PARTS, (table_bytes + slice - 1) / slice);
+  const uint64_t super = std::min<uint64_t>(len, SUPER_BYTES);
+  // every text byte starts at most one k-mer; 1.5x the mean share per partition, the excess is probed directly
+  const uint64_t region = ((super + super / 2) / n_parts + 8192) & ~(uint64_t)15;
+  const uint64_t need = region * n_parts;
+  if (c->part_buf_cap < need) {
+    if (c->d_part_buf) cudaFree(c->d_part_buf);
+    c->d_part_buf = nullptr;
+    c->part_buf_cap = 0;
+    PG_CUDA(cudaMalloc((void**)&c->d_part_buf, need * 8));
+    c->part_buf_cap = need;
+  }
+  if (!c->d_part_cursor) PG_CUDA(cudaMalloc((void**)&c->d_part_cursor, 256 * sizeof(uint32_t)));
+  pa.buf = reinterpret_cast<uint64_t*>(c->d_part_buf);
+  pa.cursor = c->d_part_cursor;
+  pa.work = c->d_part_cursor + 255;
+  pa.region_cap = (uint32_t)std::min<uint64_t>(region, 0xfffffff0u);
+  pa.n_parts = n_parts;
+  use = true;
+  return PG_OK;
+}
+
+static int part_flush(pg_counter* c, const PartArgs& pa, int op) {
+  const TableRef T = table_ref(c);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (op == PG_OP_COUNT) probe_parts_kernel<PG_OP_COUNT><<<sms * 6, 256, 0, c->stream>>>(pa, T);
+  else probe_parts_kernel<PG_OP_UPDATE><<<sms * 6, 256, 0, c->stream>>>(pa, T);
+  count_launch();
+  PG_CUDA(cudaGetLastError());
+  PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, 256 * sizeof(uint32_t), c->stream));
+  return PG_OK;
+}
+
 // Enqueues one pass over `src` (host or device text) without waiting for it: staged copies run on copy_stream ahead of
 // the kernels on c->stream.  ev0/ev1 bracket the pass on c->stream.  feed_finish() waits and checks the error flags.
-static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cudaEvent_t ev0, cudaEvent_t ev1) {
+static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cudaEvent_t ev0, cudaEvent_t ev1,
+                        const std::function<int()>* after_first_chunk = nullptr) {
   if (!c) return fail(PG_ERR_ARG, "null counter");
   if (op < 0 || op > 2) return fail(PG_ERR_ARG, "invalid op");
   if (!src && len) return fail(PG_ERR_ARG, "null text");
@@ -674,6 +936,12 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   const bool direct = on_device && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   if (!direct && len) PG_TRY(ensure_stage(c, !on_device && !pinned));
   const uint64_t step = direct ? CHUNK_BYTES : STAGE_BYTES;
+  PartArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  bool parted = false;
+  PG_TRY(part_setup(c, len, op, direct, pa, parted));
+  if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, 256 * sizeof(uint32_t), c->stream));
+  uint64_t scattered = 0;  // text bytes scattered into the partition buffers since the last flush
   for (uint64_t off = 0; off < len; off += step) {
     const uint64_t n = std::min<uint64_t>(step, len - off);
     const uint64_t nh = std::min<uint64_t>(CT_HALO, len - off - n);
@@ -698,8 +966,16 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
       PG_CUDA(cudaStreamWaitEvent(c->stream, c->stage_ready[buf], 0));
       d_text = c->d_stage[buf];
     }
-    PG_TRY(launch_chunk(c, d_text, n, n + nh, is_fastq, op));
+    PG_TRY(launch_chunk(c, d_text, n, n + nh, is_fastq, op, parted ? &pa : nullptr));
     if (!direct) PG_CUDA(cudaEventRecord(c->stage_free[buf], c->stream));
+    if (after_first_chunk && off == 0) PG_TRY((*after_first_chunk)());  // host work that overlaps the copies in flight
+    if (parted) {
+      scattered += n;
+      if (off + step >= len || scattered + step > SUPER_BYTES) {  // buffers sized for SUPER_BYTES of text
+        PG_TRY(part_flush(c, pa, op));
+        scattered = 0;
+      }
+    }
   }
   PG_CUDA(cudaEventRecord(ev1, c->stream));
   return PG_OK;
@@ -731,11 +1007,13 @@ static int feed_impl(pg_counter* c, const char* src, uint64_t len, int op) {
 
 // PRIME with the segments then UPDATE with the reads (src/jellyfishcounter.cpp:61-79), enqueued back to back: the first
 // read chunks cross PCIe while the PRIME kernels still run.  Timings land in last_prime_ms / last_feed_ms.
-int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len) {
+int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len,
+                       const std::function<int()>* overlap) {
   if (!c) return fail(PG_ERR_ARG, "null counter");
   DeviceGuard g(c->device);
   PG_TRY(feed_enqueue(c, segments, segments_len, PG_OP_PRIME, c->ev_p0, c->ev_p1));
-  PG_TRY(feed_enqueue(c, reads, reads_len, PG_OP_UPDATE, c->ev_t0, c->ev_t1));
+  PG_TRY(feed_enqueue(c, reads, reads_len, PG_OP_UPDATE, c->ev_t0, c->ev_t1, overlap));
+  if (overlap && reads_len == 0) PG_TRY((*overlap)());
   PG_TRY(feed_finish(c));
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev_p0, c->ev_p1);
@@ -825,6 +1103,8 @@ extern "C" void pg_count_destroy(pg_counter* c) {
   if (c->d_scalars) cudaFree(c->d_scalars);
   if (c->d_tile_meta) cudaFree(c->d_tile_meta);
   if (c->d_bins) cudaFree(c->d_bins);
+  if (c->d_part_buf) cudaFree(c->d_part_buf);
+  if (c->d_part_cursor) cudaFree(c->d_part_cursor);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->ev_p0) cudaEventDestroy(c->ev_p0);

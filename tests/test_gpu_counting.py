@@ -99,6 +99,28 @@ def test_incremental_feed_device_and_host_agree(oracle):
     assert g.computeKmerCoverage(12345) == o.computeKmerCoverage(12345)
 
 
+@pytest.mark.parametrize("part_kb", [0, 16, 1])
+def test_partitioned_counting_matches_oracle(oracle, monkeypatch, part_kb):
+    """Large tables are counted partition by partition (csrc/kmer_count.cu: scatter + probe_parts_kernel); the knobs shrink
+    the partition size so small inputs take that path too.  part_kb=0 is the direct path."""
+    monkeypatch.setenv("PG_COUNT_PART_KB", str(part_kb))
+    monkeypatch.setenv("PG_COUNT_PART_MIN_TEXT", "0")
+    monkeypatch.setenv("PG_COUNT_PART_STAGED", "1")  # by default only device-resident text is partitioned
+    wl = synth.make_workload(n_chrom=2, n_variants=300, n_haplotypes=4, coverage=4.0, k=31, seed=11)
+    rng = np.random.default_rng(5)
+    probes = np.concatenate([np.concatenate([p.kmer_codes for p in wl.panels])[:5000], _codes(rng, 2000, 31)])
+    _compare(oracle, wl.reads_fastq, wl.segments_fasta, 31, probes)      # PRIME + UPDATE
+    _compare(oracle, wl.reads_fastq[:400_000 // wl.record_bytes * wl.record_bytes], None, 31, probes)  # count-all (inserting) mode
+    # skew: one k-mer dominates, its partition region overflows and the excess is probed directly
+    poly = b"".join(b"@r%d\n" % i + b"A" * 150 + b"\n+\n" + b"F" * 150 + b"\n" for i in range(3000))
+    text = poly + bytes(wl.reads_fastq[:200 * wl.record_bytes])
+    g = pg.KmerCounter(text, None, 31, hash_size=600_000)
+    o = oracles.OracleCounter(oracle, text, None, 31)
+    assert g.getKmerAbundance("A" * 31) == 3000 * 120
+    assert np.array_equal(g.lookup(probes), o.lookup(probes))
+    assert g.distinct() == o.distinct()
+
+
 def test_unsupported_inputs_fail_loudly():
     with pytest.raises(pg.PgError):
         pg.KmerCounter(b"ACGT\n", None, 3, hash_size=100)          # neither FASTA nor FASTQ
