@@ -5,7 +5,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -X
 CSRC := pangenie_b200/csrc
 LIB := pangenie_b200/libpangenie_b200.so
 SRCS := $(CSRC)/host_model.cu $(CSRC)/kmer_count.cu $(CSRC)/genotype.cu
-HDRS := $(CSRC)/common.cuh $(CSRC)/hmm_kernels.cuh include/pangenie_b200.h
+HDRS := $(CSRC)/common.cuh $(CSRC)/hmm_kernels.cuh $(CSRC)/hmm_scan.cuh include/pangenie_b200.h
 
 .PHONY: all lib oracle ref clean
 all: lib oracle

@@ -515,6 +515,22 @@ struct pg_engine {
   DevBuf<double> scan_mats;
   DevBuf<uint32_t> seq_flags;
   bool scan_attr_set = false;
+  // column structure of the loaded panel (depends on the panel and the selected paths only, not on the counts): kept
+  // across calls so a resident engine does not rebuild / re-upload it for every sample
+  // ProbabilityTable(peak/4, peak*4, 2*peak, regularization) of the last sample: samples of the same k-mer coverage
+  // peak share it (about 0.15 ms of x87 long double arithmetic for a peak of 7, more for deeper samples)
+  pg_probtable table = {};
+  bool table_valid = false;
+  uint64_t panel_epoch = 0;
+  struct ColCache {
+    bool valid = false;
+    uint64_t epoch = 0;
+    std::vector<uint16_t> sel;
+    uint32_t B = 0;
+    bool scan = false;
+    std::vector<ChromCols> chroms;
+    uint32_t C = 0, nblk = 0, n_jobs = 0, n_tj = 0;
+  } cols;
   std::vector<uint8_t> h_is_column;
   pg_counter* cached_counter = nullptr;  // reused across pg_engine_run_resident calls
 };
@@ -553,6 +569,7 @@ extern "C" void pg_engine_destroy(pg_engine* e) {
   {
     DeviceGuard g(e->device);
     if (e->cached_counter) pg_count_destroy(e->cached_counter);
+    if (e->table_valid) pg_probtable_free(&e->table);
     if (e->stream) {
       cudaStreamSynchronize(e->stream);
       cudaStreamDestroy(e->stream);
@@ -635,6 +652,7 @@ static int engine_load_panels(pg_engine* e, uint32_t n_chrom, const pg_panel* pa
   e->n_chrom = n_chrom;
   e->V = (uint32_t)V;
   e->P = P;
+  ++e->panel_epoch;  // invalidates the cached column structure
   e->chrom_v0.assign(n_chrom + 1, 0);
   for (uint32_t c = 0; c < n_chrom; ++c) e->chrom_v0[c + 1] = e->chrom_v0[c] + panels[c].n_variants;
   cudaStream_t s = e->stream;
@@ -765,8 +783,23 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   if (P > HMM_PMAX) return fail(PG_ERR_ARG, "more than 256 selected paths: use path sub-sampling (-a) or haplotype sampling (-x)");
   TileCfg cfg;
   if (!pick_cfg(P, cfg)) return fail(PG_ERR_ARG, "no kernel configuration for this number of paths");
-  PG_TRY(e->sel.reserve(P));
-  PG_CUDA(cudaMemcpyAsync(e->sel.p, sel.data(), P * 2, cudaMemcpyHostToDevice, s));
+  // checkpoint schedule: P <= 9 propagates a basis through every block in parallel (hmm_scan.cuh), larger path
+  // sets walk the chains sequentially (skeleton_kernel).  PG_SKELETON=seq|scan and PG_HMM_B are tuning/test knobs.
+  const char* skel_env = getenv("PG_SKELETON");
+  const bool scan_candidate = P <= (uint32_t)SCAN_CPL && !(skel_env && skel_env[0] == 's' && skel_env[1] == 'e');
+  uint32_t B = 64;
+  if (scan_candidate) B = 64; else if (P <= 12) B = 256; else if (P <= 36) B = 128;
+  if (const char* be = getenv("PG_HMM_B")) {
+    const long v = atol(be);
+    if (v >= 2 && v <= HMM_BMAX) B = (uint32_t)v;
+  }
+  pg_engine::ColCache& cc = e->cols;
+  const bool cached = cc.valid && cc.epoch == e->panel_epoch && cc.sel == sel && cc.B == B && cc.scan == scan_candidate;
+  if (!cached) {
+    cc.valid = false;
+    PG_TRY(e->sel.reserve(P));
+    PG_CUDA(cudaMemcpyAsync(e->sel.p, sel.data(), P * 2, cudaMemcpyHostToDevice, s));
+  }
 
   cudaEventRecord(e->ev[0], s);
   TableDev td;
@@ -778,49 +811,47 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   PG_TRY(e->is_column.reserve(std::max<uint32_t>(V, 1)));
   PG_TRY(e->post.reserve(std::max<uint64_t>(e->GL, 1)));
   PG_CUDA(cudaMemsetAsync(e->post.p, 0, std::max<uint64_t>(e->GL, 1) * 8, s));
-  e->h_is_column.assign(V, 0);
-  if (V) {
-    const int grid = (int)std::min<uint64_t>(((uint64_t)V * 32 + 255) / 256, (uint64_t)e->sm_count * 16);
-    column_flag_kernel<<<grid, 256, 0, s>>>(panel_view(e), e->sel.p, P, e->is_column.p);
-    count_launch();
-    PG_CUDA(cudaMemcpyAsync(e->h_is_column.data(), e->is_column.p, V, cudaMemcpyDeviceToHost, s));
-  }
-  PG_CUDA(cudaStreamSynchronize(s));
-  // host: column list, chromosome ranges, blocks, jobs
-  std::vector<uint32_t> col_variant, col_cbeg, col_cend, variant_col(std::max<uint32_t>(V, 1), 0);
-  std::vector<ChromCols> chroms(e->n_chrom);
-  // checkpoint schedule: P <= 9 propagates a basis through every block in parallel (hmm_scan.cuh), larger path
-  // sets walk the chains sequentially (skeleton_kernel).  PG_SKELETON=seq|scan and PG_HMM_B are tuning/test knobs.
-  const char* skel_env = getenv("PG_SKELETON");
-  const bool scan_candidate = P <= (uint32_t)SCAN_CPL && !(skel_env && skel_env[0] == 's' && skel_env[1] == 'e');
-  uint32_t B = 64;
-  if (scan_candidate) B = 64; else if (P <= 12) B = 256; else if (P <= 36) B = 128;
-  if (const char* be = getenv("PG_HMM_B")) {
-    const long v = atol(be);
-    if (v >= 2 && v <= HMM_BMAX) B = (uint32_t)v;
-  }
   std::vector<uint2> jobs;
-  uint32_t nblk = 0;
-  for (uint32_t c = 0; c < e->n_chrom; ++c) {
-    const uint32_t cb = (uint32_t)col_variant.size();
-    for (uint32_t v = e->chrom_v0[c]; v < e->chrom_v0[c + 1]; ++v)
-      if (e->h_is_column[v]) {
-        variant_col[v] = (uint32_t)col_variant.size();
-        col_variant.push_back(v);
-      }
-    const uint32_t ce = (uint32_t)col_variant.size();
-    chroms[c].col_begin = cb;
-    chroms[c].col_end = ce;
-    chroms[c].blk_begin = nblk;
-    chroms[c].n_blocks = (ce - cb + B - 1) / B;
-    for (uint32_t k = 0; k < chroms[c].n_blocks; ++k) jobs.push_back(make_uint2(c, k));
-    nblk += chroms[c].n_blocks;
-    for (uint32_t t = cb; t < ce; ++t) {
-      col_cbeg.push_back(cb);
-      col_cend.push_back(ce);
+  std::vector<uint32_t> col_variant, col_cbeg, col_cend, variant_col;
+  if (!cached) {
+    e->h_is_column.assign(V, 0);
+    if (V) {
+      const int grid = (int)std::min<uint64_t>(((uint64_t)V * 32 + 255) / 256, (uint64_t)e->sm_count * 16);
+      column_flag_kernel<<<grid, 256, 0, s>>>(panel_view(e), e->sel.p, P, e->is_column.p);
+      count_launch();
+      PG_CUDA(cudaMemcpyAsync(e->h_is_column.data(), e->is_column.p, V, cudaMemcpyDeviceToHost, s));
     }
+    PG_CUDA(cudaStreamSynchronize(s));
+    // host: column list, chromosome ranges, blocks, jobs
+    variant_col.assign(std::max<uint32_t>(V, 1), 0);
+    cc.chroms.assign(e->n_chrom, ChromCols());
+    uint32_t nb_run = 0;
+    for (uint32_t c = 0; c < e->n_chrom; ++c) {
+      const uint32_t cb = (uint32_t)col_variant.size();
+      for (uint32_t v = e->chrom_v0[c]; v < e->chrom_v0[c + 1]; ++v)
+        if (e->h_is_column[v]) {
+          variant_col[v] = (uint32_t)col_variant.size();
+          col_variant.push_back(v);
+        }
+      const uint32_t ce = (uint32_t)col_variant.size();
+      cc.chroms[c].col_begin = cb;
+      cc.chroms[c].col_end = ce;
+      cc.chroms[c].blk_begin = nb_run;
+      cc.chroms[c].n_blocks = (ce - cb + B - 1) / B;
+      for (uint32_t k = 0; k < cc.chroms[c].n_blocks; ++k) jobs.push_back(make_uint2(c, k));
+      nb_run += cc.chroms[c].n_blocks;
+      for (uint32_t t = cb; t < ce; ++t) {
+        col_cbeg.push_back(cb);
+        col_cend.push_back(ce);
+      }
+    }
+    cc.C = (uint32_t)col_variant.size();
+    cc.nblk = nb_run;
+    cc.n_jobs = (uint32_t)jobs.size();
   }
-  const uint32_t C = (uint32_t)col_variant.size();
+  const std::vector<ChromCols>& chroms = cc.chroms;
+  const uint32_t nblk = cc.nblk;
+  const uint32_t C = cc.C;
   e->tm.hmm_columns = C;
   const uint32_t stride = (uint32_t)desc_bytes(P);
   const size_t PP = (size_t)cfg.CPL * cfg.RPW * cfg.nthreads;  // doubles per stored state (thread-major layout)
@@ -829,7 +860,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   PG_TRY(e->col_cend.reserve(std::max<uint32_t>(C, 1)));
   PG_TRY(e->variant_col.reserve(std::max<uint32_t>(V, 1)));
   PG_TRY(e->chroms.reserve(e->n_chrom));
-  PG_TRY(e->jobs.reserve(std::max<size_t>(jobs.size(), 1)));
+  PG_TRY(e->jobs.reserve(std::max<size_t>(cc.n_jobs, 1)));
   PG_TRY(e->desc.reserve(std::max<size_t>((size_t)C * stride, 16)));
   PG_TRY(e->tot_fwd.reserve(std::max<uint32_t>(C, 1)));
   PG_TRY(e->tot_bwd.reserve(std::max<uint32_t>(C, 1)));
@@ -840,14 +871,17 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   PG_TRY(e->quality.reserve(std::max<uint32_t>(V, 1)));
   PG_TRY(e->unique_kmers.reserve(std::max<uint32_t>(V, 1)));
   PG_TRY(e->coverage_out.reserve(std::max<uint32_t>(V, 1)));
-  if (C) {
-    PG_CUDA(cudaMemcpyAsync(e->col_variant.p, col_variant.data(), C * 4, cudaMemcpyHostToDevice, s));
-    PG_CUDA(cudaMemcpyAsync(e->col_cbeg.p, col_cbeg.data(), C * 4, cudaMemcpyHostToDevice, s));
-    PG_CUDA(cudaMemcpyAsync(e->col_cend.p, col_cend.data(), C * 4, cudaMemcpyHostToDevice, s));
-    PG_CUDA(cudaMemcpyAsync(e->jobs.p, jobs.data(), jobs.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+  if (!cached) {
+    if (C) {
+      PG_CUDA(cudaMemcpyAsync(e->col_variant.p, col_variant.data(), C * 4, cudaMemcpyHostToDevice, s));
+      PG_CUDA(cudaMemcpyAsync(e->col_cbeg.p, col_cbeg.data(), C * 4, cudaMemcpyHostToDevice, s));
+      PG_CUDA(cudaMemcpyAsync(e->col_cend.p, col_cend.data(), C * 4, cudaMemcpyHostToDevice, s));
+      PG_CUDA(cudaMemcpyAsync(e->jobs.p, jobs.data(), jobs.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    }
+    if (V) PG_CUDA(cudaMemcpyAsync(e->variant_col.p, variant_col.data(), V * 4, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaMemcpyAsync(e->chroms.p, chroms.data(), e->n_chrom * sizeof(ChromCols), cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaStreamSynchronize(s));  // the host vectors above are locals
   }
-  if (V) PG_CUDA(cudaMemcpyAsync(e->variant_col.p, variant_col.data(), V * 4, cudaMemcpyHostToDevice, s));
-  PG_CUDA(cudaMemcpyAsync(e->chroms.p, chroms.data(), e->n_chrom * sizeof(ChromCols), cudaMemcpyHostToDevice, s));
   PG_CUDA(cudaMemsetAsync(e->work_counter.p, 0, 16, s));
 
   cudaEventRecord(e->ev[2], s);
@@ -866,7 +900,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     cp.P = P; cp.B = B; cp.desc = e->desc.p; cp.desc_stride = stride; cp.chroms = e->chroms.p;
     cp.ckpt_fwd = e->ckpt_fwd.p; cp.ckpt_bwd = e->ckpt_bwd.p; cp.tot_fwd = e->tot_fwd.p; cp.tot_bwd = e->tot_bwd.p;
     cp.post = e->post.p; cp.gl_off = e->gl_off.p; cp.allele_off = e->allele_off.p; cp.allele_ids = e->allele_ids.p;
-    cp.work_counter = e->work_counter.p; cp.jobs = e->jobs.p; cp.n_jobs = (uint32_t)jobs.size();
+    cp.work_counter = e->work_counter.p; cp.jobs = e->jobs.p; cp.n_jobs = cc.n_jobs;
     cp.seq_flags = nullptr;
     bool need_skel = false;
     for (auto& ch : chroms) need_skel |= ch.n_blocks > 1;
@@ -878,7 +912,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
       const uint32_t NB = P * (P + 1) / 2;
       std::vector<TJob> tj;
       std::vector<ScanChrom> sch(e->n_chrom);
-      for (uint32_t c = 0; c < e->n_chrom; ++c) {
+      for (uint32_t c = 0; c < e->n_chrom && !cached; ++c) {
         const ChromCols& ch = chroms[c];
         sch[c].n_tj = ch.n_blocks > 1 ? ch.n_blocks - 1 : 0;
         sch[c].pad = 0;
@@ -909,18 +943,21 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
         }
       }
       constexpr uint32_t G = 32 / SCAN_CPL;
-      sp.n_tj = (uint32_t)tj.size();
+      if (!cached) cc.n_tj = (uint32_t)tj.size();
+      sp.n_tj = cc.n_tj;
       sp.n_groups = (NB + G - 1) / G;
       sp.n_items = sp.n_tj * sp.n_groups;
       sp.mat_stride = ((NB + 1u) * NB + 1u) & ~1u;
-      PG_TRY(e->tjobs.reserve(tj.size()));
+      PG_TRY(e->tjobs.reserve(std::max<size_t>(cc.n_tj, 1)));
       PG_TRY(e->scan_chroms.reserve(e->n_chrom));
       PG_TRY(e->scan_mats.reserve((size_t)sp.n_tj * sp.mat_stride));
       PG_TRY(e->seq_flags.reserve(e->n_chrom));
-      PG_CUDA(cudaMemcpyAsync(e->tjobs.p, tj.data(), tj.size() * sizeof(TJob), cudaMemcpyHostToDevice, s));
-      PG_CUDA(cudaMemcpyAsync(e->scan_chroms.p, sch.data(), sch.size() * sizeof(ScanChrom), cudaMemcpyHostToDevice, s));
+      if (!cached) {
+        PG_CUDA(cudaMemcpyAsync(e->tjobs.p, tj.data(), tj.size() * sizeof(TJob), cudaMemcpyHostToDevice, s));
+        PG_CUDA(cudaMemcpyAsync(e->scan_chroms.p, sch.data(), sch.size() * sizeof(ScanChrom), cudaMemcpyHostToDevice, s));
+        PG_CUDA(cudaStreamSynchronize(s));  // tj / sch are stack-owned host vectors
+      }
       PG_CUDA(cudaMemsetAsync(e->seq_flags.p, 0, e->n_chrom * sizeof(uint32_t), s));
-      PG_CUDA(cudaStreamSynchronize(s));  // tj / sch are stack-owned host vectors
       sp.tjobs = e->tjobs.p; sp.mats = e->scan_mats.p; sp.chroms = e->scan_chroms.p;
       sp.seq_flags = e->seq_flags.p;
       cp.seq_flags = e->seq_flags.p;
@@ -938,7 +975,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     }
 #undef PG_OCC
     if (occ < 1) occ = 1;
-    const int grid_blocks = (int)std::min<uint64_t>(jobs.size(), (uint64_t)e->sm_count * occ);
+    const int grid_blocks = (int)std::min<uint64_t>(cc.n_jobs, (uint64_t)e->sm_count * occ);
     PG_TRY(e->block_buf.reserve((size_t)grid_blocks * B * PP));
     cp.block_buf = e->block_buf.p;
     cudaError_t le;
@@ -1006,6 +1043,13 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]); e->tm.finalize_ms = ms;
   e->tm.hmm_block_launches = block_launches;
   e->tm.hmm_scan_used = scan_used;
+  if (!cached) {  // everything uploaded and consumed without error: later calls on the same panel may reuse it
+    cc.epoch = e->panel_epoch;
+    cc.sel = sel;
+    cc.B = B;
+    cc.scan = scan_candidate;
+    cc.valid = true;
+  }
   return PG_OK;
 }
 
@@ -1063,6 +1107,20 @@ static int engine_fetch_counts(pg_engine* e, uint32_t n_chrom, pg_panel* panels)
     if (panels[c].coverage) PG_CUDA(cudaMemcpyAsync(panels[c].coverage, e->coverage.p + e->chrom_v0[c], nv * 2, cudaMemcpyDeviceToHost, e->stream));
   }
   PG_CUDA(cudaStreamSynchronize(e->stream));
+  return PG_OK;
+}
+
+// the sample's ProbabilityTable (src/commands.cpp:846), rebuilt only when the peak or the regularisation changes
+static int engine_table(pg_engine* e, uint64_t peak, double regularization, const pg_probtable** out) {
+  const uint16_t cmin = (uint16_t)(peak / 4), cmax = (uint16_t)(peak * 4), nmax = (uint16_t)(2 * peak);
+  if (!(e->table_valid && e->table.cov_min == cmin && e->table.cov_max == cmax && e->table.count_max == nmax &&
+        e->table.regularization == regularization)) {
+    if (e->table_valid) pg_probtable_free(&e->table);
+    e->table_valid = false;
+    PG_TRY(pg_probtable_init(&e->table, cmin, cmax, nmax, regularization));
+    e->table_valid = true;
+  }
+  *out = &e->table;
   return PG_OK;
 }
 
@@ -1171,19 +1229,15 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
   PG_TRY(pg_count_compute_histogram(c, 10000, in->segments != nullptr, in->histogram_path, &peak));
   if (kmer_abundance_peak) *kmer_abundance_peak = peak;
   // 3) ProbabilityTable(peak/4, peak*4, 2*peak, regularization) (:846)
-  pg_probtable table;
-  PG_TRY(pg_probtable_init(&table, (uint16_t)(peak / 4), (uint16_t)(peak * 4), (uint16_t)(2 * peak), in->regularization));
-  struct TGuard {
-    pg_probtable* t;
-    ~TGuard() { pg_probtable_free(t); }
-  } tguard{&table};
+  const pg_probtable* table = nullptr;
+  PG_TRY(engine_table(e, peak, in->regularization, &table));
   tr.mark("histogram+table");
   // 4) fill + 5) HMM, panel uploaded once
   if (!panels_loaded) PG_TRY(engine_load_panels(e, n_chrom, panels, results, false, true));
   tr.mark("load_panels");
   PG_TRY(engine_fill(e, c, peak));
   tr.mark("fill");
-  PG_TRY(engine_hmm(e, &table, params));
+  PG_TRY(engine_hmm(e, table, params));
   tr.mark("hmm");
   PG_TRY(engine_fetch_counts(e, n_chrom, panels));
   PG_TRY(engine_fetch_results(e, n_chrom, panels, results));
@@ -1206,17 +1260,13 @@ static int engine_after_count(pg_engine* e, const pg_counter* c, bool largest_pe
   cudaEventElapsedTime(&hms, h0, h1);
   if (st != PG_OK) return st;
   if (kmer_abundance_peak) *kmer_abundance_peak = peak;
-  pg_probtable table;
-  PG_TRY(pg_probtable_init(&table, (uint16_t)(peak / 4), (uint16_t)(peak * 4), (uint16_t)(2 * peak), regularization));
-  struct TGuard {
-    pg_probtable* t;
-    ~TGuard() { pg_probtable_free(t); }
-  } tguard{&table};
+  const pg_probtable* table = nullptr;
+  PG_TRY(engine_table(e, peak, regularization, &table));
   tr.mark("histogram+table");
   PG_TRY(engine_fill(e, c, peak));
   tr.mark("fill");
   const double fill_ms = e->tm.fill_ms;
-  PG_TRY(engine_hmm(e, &table, params));
+  PG_TRY(engine_hmm(e, table, params));
   tr.mark("hmm");
   e->tm.fill_ms = fill_ms;
   e->tm.histogram_ms = hms;

@@ -24,7 +24,7 @@ namespace pg {
 
 constexpr int SCAN_CPL = 9;                                  // largest P handled by the scan path
 constexpr int SCAN_NB = SCAN_CPL * (SCAN_CPL + 1) / 2;       // 45 basis elements / upper-triangle cells
-constexpr int SCAN_THREADS = 64;                             // scan_kernel CTA (>= SCAN_NB)
+constexpr int SCAN_THREADS = 192;                            // scan_kernel CTA (>= 4 * SCAN_NB)
 constexpr int BASIS_WARPS = 4;                               // warps per basis_kernel CTA
 
 struct TJob {
@@ -93,7 +93,7 @@ struct ColEm {
 // 1. basis chains.  One warp runs G = 32/CPL chains of the same transfer job: lane = chain * CPL + row.
 // -------------------------------------------------------------------------------------------------
 template <int CPL>
-__global__ void __launch_bounds__(BASIS_WARPS * 32) basis_kernel(const ChainParams p, const ScanParams sp) {
+__global__ void __launch_bounds__(BASIS_WARPS * 32, 8) basis_kernel(const ChainParams p, const ScanParams sp) {
   constexpr int G = 32 / CPL;
   __shared__ double rsm[BASIS_WARPS][2][32];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,14 +154,27 @@ __global__ void __launch_bounds__(BASIS_WARPS * 32) basis_kernel(const ChainPara
     const double ca = ta * sc, cb = tb * sc, cc = tc * T * sc;
     const double rho = cb * myR + cc;
     double a0 = 0.0, a1 = 0.0;
+    if (em.A <= 2) {  // (warp-uniform) biallelic column: the emission is a select on the path's allele bit
+      const uint32_t okbits = rok ? cmask : 0u;
 #pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-      const bool ok = rok && ((cmask >> s) & 1u);
-      const double pre = fma(ca, x[s], fma(cb, R[s], rho));
-      const double v = ok ? pre * em.at(s, ok) : 0.0;
-      x[s] = v;
-      if (s & 1) a1 += v;
-      else a0 += v;
+      for (int s = 0; s < CPL; ++s) {
+        const double pre = fma(ca, x[s], fma(cb, R[s], rho));
+        const double e = ((em.bits >> s) & 1u) ? em.er1 : em.er0;
+        const double v = ((okbits >> s) & 1u) ? pre * e : 0.0;
+        x[s] = v;
+        if (s & 1) a1 += v;
+        else a0 += v;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < CPL; ++s) {
+        const bool ok = rok && ((cmask >> s) & 1u);
+        const double pre = fma(ca, x[s], fma(cb, R[s], rho));
+        const double v = ok ? pre * em.at(s, ok) : 0.0;
+        x[s] = v;
+        if (s & 1) a1 += v;
+        else a0 += v;
+      }
     }
     myR = a0 + a1;
     buf ^= 1;
@@ -182,7 +195,8 @@ __global__ void __launch_bounds__(BASIS_WARPS * 32) basis_kernel(const ChainPara
 // 2. checkpoint scan.  grid = (n_chrom, 2): y = 0 forward, y = 1 backward; one upper-triangle cell per thread.
 //    Checkpoints are written in the thread-major layout of Chain<1, CPL, 1, 32> (cell (i,j) at [j*32 + i]).
 // -------------------------------------------------------------------------------------------------
-constexpr int SCAN_RING = 4;  // transfer matrices in flight (L2 -> shared memory), one cp.async group each
+constexpr int SCAN_RING = 4;   // transfer matrices in flight (L2 -> shared memory), one cp.async group each
+constexpr int SCAN_SPLIT = 4;  // lanes sharing one cell: each sums a quarter of the basis range
 template <int CPL>
 struct ScanSmem {
   static constexpr int NBMAX = CPL * (CPL + 1) / 2;
@@ -190,10 +204,12 @@ struct ScanSmem {
   double mat[SCAN_RING][MATMAX];
   double st[NBMAX];  // current state, upper triangle
   double w[NBMAX];
-  double tot[2];
-  int key[2];
+  int key[SCAN_THREADS / 32];
 };
 
+// One step: new_state[c] = sum_b w_b * M[b][c], w_b = state[b] * 2^(E_b - kmax).  The weights only depend on RELATIVE
+// exponents and are renormalised every step (largest term in [1,2)), so the state never needs a normalisation of its own:
+// its magnitude is that of the basis images, which basis_kernel keeps near 1.  Three barriers per step.
 template <int CPL>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p, const ScanParams sp) {
   extern __shared__ __align__(16) unsigned char scan_smem_raw[];
@@ -219,11 +235,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
   };
   for (uint32_t q = 0; q + 1 < SCAN_RING; ++q) prefetch(q);
 
-  // my cell (ci <= cj)
+  // my cell (ci <= cj) and my share of the basis range
+  const int cell = tid / SCAN_SPLIT, part = tid % SCAN_SPLIT;
+  const bool cell_ok = cell < NB;
   int ci = 0, cj = 0;
-  const bool cell_ok = tid < NB;
   {
-    int q = cell_ok ? tid : 0;
+    int q = cell_ok ? cell : 0;
     while (q >= P - ci) {
       q -= P - ci;
       ++ci;
@@ -231,25 +248,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
     cj = ci + q;
   }
   // initial state: the chain's first column without transition (pre = 1): F = e'_{c0}, Y = e'_{c1-1}
-  {
+  if (part == 0) {
     const int t = dir ? (int)cc.col_end - 1 : (int)cc.col_begin;
     const double* d = reinterpret_cast<const double*>(p.desc + (size_t)(uint32_t)t * p.desc_stride);
     ColEm em;
     em.load(d, ci, cell_ok);
-    if (cell_ok) sm.st[tid] = em.at(cj, true);
+    if (cell_ok) sm.st[cell] = em.at(cj, true);
   }
-  __syncthreads();
 
-  for (uint32_t q = 0; q < sc.n_tj; ++q) {
-    prefetch(q + SCAN_RING - 1);  // its ring slot was last read in step q - 1 (barrier at the end of that step)
-    cp_async_wait<SCAN_RING - 1>();  // all but the newest SCAN_RING - 1 groups are complete: matrix q has landed
-    __syncthreads();
+  for (uint32_t q = 0; q <= sc.n_tj; ++q) {
+    cp_async_wait<SCAN_RING - 2>();  // all but the newest SCAN_RING - 2 groups are complete: matrix q has landed
+    __syncthreads();                 // ... the state written at the end of step q - 1 is visible, and every warp is done
+                                     // reading matrix q - 1, whose ring slot the next prefetch overwrites
+    prefetch(q + SCAN_RING - 1);
+    const double* M = sm.mat[q % SCAN_RING];
     // ---- weights: coefficient of basis b = state cell b, times the row's power-of-two scale, relative to the largest
     double coef = 0.0;
     int key = INT_MIN, Eb = 0;
-    if (cell_ok) {
+    if (tid < NB) {
       coef = sm.st[tid];
-      Eb = (int)sm.mat[q % SCAN_RING][NB * NB + tid];
+      Eb = q < sc.n_tj ? (int)M[NB * NB + tid] : 0;
       if (coef > 0.0) key = (((__double2hiint(coef) >> 20) & 0x7ff) - 1023) + Eb;
     }
     int kmax = key;
@@ -257,50 +275,48 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
     for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     if (lane == 0) sm.key[wid] = kmax;
     __syncthreads();
-    kmax = max(sm.key[0], sm.key[1]);
-    if (cell_ok) {
-      double wv = 0.0;
-      if (coef > 0.0) {
-        const int sh = Eb - kmax;  // <= 0 up to the coefficient's own exponent
-        wv = sh < -2000 ? 0.0 : scalbn(coef, sh);
-      }
-      sm.w[tid] = wv;
-    }
-    __syncthreads();
-    // ---- new cell value
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (cell_ok) {
-      const double* m = &sm.mat[q % SCAN_RING][tid];
-      int b = 0;
-      for (; b + 3 < NB; b += 4) {
-        a0 = fma(sm.w[b], m[(size_t)b * NB], a0);
-        a1 = fma(sm.w[b + 1], m[(size_t)(b + 1) * NB], a1);
-        a2 = fma(sm.w[b + 2], m[(size_t)(b + 2) * NB], a2);
-        a3 = fma(sm.w[b + 3], m[(size_t)(b + 3) * NB], a3);
-      }
-      for (; b < NB; ++b) a0 = fma(sm.w[b], m[(size_t)b * NB], a0);
-    }
-    double v = (a0 + a1) + (a2 + a3);
-    double tot = cell_ok ? (ci == cj ? v : 2.0 * v) : 0.0;
+    kmax = sm.key[0];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) sm.tot[wid] = tot;
-    __syncthreads();  // also: everyone is done reading st[] / w[] / the matrix
-    const double T = sm.tot[0] + sm.tot[1];
-    if (!(T > 0.0)) {  // dead checkpoint: the uniform replacement is not linear -> sequential recomputation
+    for (int i = 1; i < SCAN_THREADS / 32; ++i) kmax = max(kmax, sm.key[i]);
+    if (kmax == INT_MIN) {  // dead state: the reference's uniform replacement is not linear -> sequential recomputation
       if (tid == 0) atomicOr(sp.seq_flags + chrom, 1u);
       cp_async_wait<0>();
       return;
     }
-    v *= pow2_scale_of(T);
+    if (q == sc.n_tj) break;  // (the extra round only checks the last checkpoint)
+    if (tid < NB) {
+      double wv = 0.0;
+      if (coef > 0.0) {
+        const int sh = Eb - kmax;  // <= 0 up to the coefficient's own exponent; the product is <= 2
+        wv = sh < -1000 ? 0.0 : coef * __hiloint2double((1023 + sh) << 20, 0);  // exact 2^sh; terms below 2^-1000 are noise
+      }
+      sm.w[tid] = wv;
+    }
+    __syncthreads();
+    // ---- new cell value: SCAN_SPLIT lanes per cell, each over b = part, part + SCAN_SPLIT, ...
+    double a0 = 0.0, a1 = 0.0;
     if (cell_ok) {
-      sm.st[tid] = v;
+      const double* m = M + cell;
+      constexpr int ITER = (ScanSmem<CPL>::NBMAX + SCAN_SPLIT - 1) / SCAN_SPLIT;
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {  // static trip count: all loads of the step issue back to back
+        const int b = part + i * SCAN_SPLIT;
+        const double wv = b < NB ? sm.w[b] : 0.0;
+        const double mv = b < NB ? m[b * NB] : 0.0;
+        if (i & 1) a1 = fma(wv, mv, a1);
+        else a0 = fma(wv, mv, a0);
+      }
+    }
+    double v = a0 + a1;
+#pragma unroll
+    for (int o = 1; o < SCAN_SPLIT; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (cell_ok && part == 0) {
+      sm.st[cell] = v;  // read again only after the next barrier; the readers of this step passed the second one
       const uint32_t out_blk = dir ? sc.out_first[1] - q : sc.out_first[0] + q;
       double* out = (dir ? p.ckpt_bwd : p.ckpt_fwd) + (size_t)out_blk * p.state_stride;
       out[(size_t)cj * 32 + ci] = v;
       if (ci != cj) out[(size_t)ci * 32 + cj] = v;
     }
-    __syncthreads();
   }
   cp_async_wait<0>();
 }

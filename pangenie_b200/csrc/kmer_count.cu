@@ -229,12 +229,13 @@ __device__ __forceinline__ int block_exscan_max(int v, int* s_warp) {
 // ------------------------------------------------------------------------------------------------
 // Slow path of an INSERTING operation (PRIME / COUNT): `b` is the bucket to (re)examine, position by position with
 // FRESH reads (the snapshot taken by the fast path may be stale after a lost CAS).  On success `slot` = 4*bucket + pos.
+// Positions < j0 of the FIRST bucket are known to hold other keys (keys never change once set), so the walk starts at j0.
 template <int OP>
 __device__ __noinline__ bool resolve_insert(uint64_t kmer, uint64_t b, uint64_t& slot, KmerBucket* tab, uint64_t nb,
-                                            unsigned long long* scalars, uint32_t& inserted) {
-  for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
+                                            unsigned long long* scalars, uint32_t& inserted, int j0 = 0) {
+  for (uint32_t probes = 0; probes < (1u << 20); ++probes, j0 = 0) {
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = j0; j < 4; ++j) {
       unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tab[b].key[j]);
       if (cur == EMPTY_KEY) {
         cur = atomicCAS(&tab[b].key[j], (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
@@ -376,7 +377,9 @@ __device__ __forceinline__ void probe4(const uint64_t (&cn)[4], uint32_t vm, con
         }
       } else {
         uint64_t slot = 0;
-        if (resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, T.scalars, inserted)) {
+        // first empty position of the snapshot: everything before it is occupied by other keys
+        const int j0 = full ? 0 : (ka[i].x == EMPTY_KEY ? 0 : ka[i].y == EMPTY_KEY ? 1 : kb[i].x == EMPTY_KEY ? 2 : 3);
+        if (resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, T.scalars, inserted, j0)) {
           hitm |= 1u << i;
           bkt[i] = slot;
         }

@@ -52,3 +52,30 @@ def test_fill_counts_standalone(engine, oracle):
     o.fill_counts(peak, wl.panels)
     for p, (c, cv) in zip(wl.panels, got):
         assert np.array_equal(p.kmer_counts, c) and np.array_equal(p.coverage, cv)
+
+
+def test_resident_engine_reuses_the_panel_across_samples(engine, oracle):
+    """pg_engine_load once, then several samples through pg_engine_run_resident: the cached column structure, the
+    reused counter and the scan/sequential checkpoint paths must not leak state from one sample to the next."""
+    import torch
+    wl = synth.make_workload(n_chrom=2, n_variants=700, n_haplotypes=8, coverage=10.0, seed=31)
+    kw = dict(recombrate=1.26, effective_N=1e-5)
+    want, peak_o = _oracle_pipeline(oracle, wl, **kw)
+    segs_d = torch.from_numpy(wl.segments_fasta).cuda()
+    reads_d = torch.from_numpy(wl.reads_fastq).cuda()
+    half = (len(wl.reads_fastq) // wl.record_bytes // 2) * wl.record_bytes
+    half_d = torch.from_numpy(wl.reads_fastq[:half].copy()).cuda()
+    engine.load(wl.panels)
+    for reads, full in ((reads_d, True), (half_d, False), (reads_d, True)):
+        peak = engine.run_resident(reads, segs_d, k=wl.k, **kw)
+        got = engine.fetch()
+        if full:
+            assert peak == peak_o
+            for i, (g, w) in enumerate(zip(got, want)):
+                assert_results_close(g, w, label=f"chromosome {i}")
+    # a different path subset on the same loaded panel invalidates the cached column structure
+    sub = dict(kw, only_paths=[0, 2, 3, 5])
+    want_sub, _ = _oracle_pipeline(oracle, wl, **sub)
+    engine.run_resident(reads_d, segs_d, k=wl.k, **sub)
+    for i, (g, w) in enumerate(zip(engine.fetch(), want_sub)):
+        assert_results_close(g, w, label=f"subset, chromosome {i}")
