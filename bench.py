@@ -48,6 +48,11 @@ WORKLOAD_TEXT = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture, summed over its
+# launches of ONE step (like `achieved`, which is per step): profiles/r1_ncu_cfg2.md (two UPDATE launch sets per step)
+NCU_TRAFFIC = {("cfg2", "count_tile_kernel<UPDATE>"): (1.315594e9 + 0.509737e9) + (1.150345e9 + 0.442476e9)}
+
+
 def fb_bytes_per_column(P: int, A: int = 2) -> float:
     """B_fb = 2*8*P^2 + 2*2*P + 2*8*A^2 + 8 + 8*A(A+1)/2."""
     return 2 * 8 * P * P + 2 * 2 * P + 2 * 8 * A * A + 8 + 8 * A * (A + 1) / 2
@@ -138,6 +143,9 @@ def cpu_pipeline(wl, threads: int, sample_bytes: int, filled_panels_ok: bool):
     rec = wl.record_bytes
     total = len(wl.reads_fastq)
     sample = min(total, max(rec, (sample_bytes // rec) * rec))
+    if total <= (512 << 20):
+        sample = total  # small workload: count every read (a few seconds), so fill + HMM see the real counts
+        filled_panels_ok = False
     t0 = time.perf_counter()
     oc = oracles.OracleCounter(oracle, None, None, wl.k)
     oc.feed(wl.segments_fasta, pg.PG_OP_PRIME, threads=threads)
@@ -149,10 +157,18 @@ def cpu_pipeline(wl, threads: int, sample_bytes: int, filled_panels_ok: bool):
     # the HMM needs counts of the FULL read set: taken from the panels as filled by the GPU run (bit-identical
     # to the oracle's, tests/test_gpu_pipeline.py) so the CPU arm genotypes the same filled panel
     t0 = time.perf_counter()
+    synthetic_counts = False
     if not filled_panels_ok:
         peak = oc.computeHistogram(10000, True)
         oc.fill_counts(peak, wl.panels)
     t_fill = time.perf_counter() - t0
+    if not filled_panels_ok and sample < total:
+        # counts of a read SAMPLE are too low to be representative for the HMM (most lookups would leave the table):
+        # time the HMM on Poisson counts of the workload's nominal coverage instead
+        from pangenie_b200 import synth
+        cov = WORKLOADS[[k for k, v in WORKLOADS.items() if v[1] == wl.n_variants][0]][3]
+        synth.fill_synthetic_counts(np.random.default_rng(1), wl, peak=max(int(cov * 0.75), 4))
+        synthetic_counts = True
     peak = max(int(np.median(np.concatenate([p.coverage for p in wl.panels]))), 4)
     table = pg.ProbabilityTable(peak // 4, peak * 4, 2 * peak, 0.01)
     hthreads = min(threads, len(wl.panels))
@@ -170,7 +186,8 @@ def cpu_pipeline(wl, threads: int, sample_bytes: int, filled_panels_ok: bool):
         "sample": (f"emission+HMM: reference hmm.cpp on the full panel, {hthreads} thread(s) (one per chromosome, commands.cpp:949-978), "
                    f"{t_hmm:.3f}s; counting: CPU restatement of the jellyfish path (not libjellyfish), {threads} threads, PRIME full segments "
                    f"{t_prime:.2f}s + UPDATE on the first {sample / 1e6:.1f} MB of {total / 1e6:.1f} MB reads {t_update_sample:.2f}s "
-                   f"extrapolated linearly to {t_update:.2f}s; fill {t_fill:.3f}s"),
+                   f"extrapolated linearly to {t_update:.2f}s; fill {t_fill:.3f}s"
+                   + ("; HMM timed on synthetic Poisson counts (the sampled counts are not representative)" if synthetic_counts else "")),
         "seconds": {"prime": t_prime, "update_extrapolated": t_update, "fill": t_fill, "hmm": t_hmm},
     }
 
@@ -406,7 +423,9 @@ def main():
         kk["gbs"] = kk["alg_bytes"] / (kk["ms"] * 1e-3) / 1e9 if kk["ms"] > 0 else 0.0
     dom = max(("count_tile_kernel<UPDATE>", "block_kernel (forward-backward)"), key=lambda n: kernels[n]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": kernels[dom]["gbs"] / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["gbs"] / peak_gbs, "traffic": NCU_TRAFFIC.get((args.workload, dom)),
+                "traffic_source": "profiles/r1_ncu_cfg2.md (ncu --set full, per step)" if (args.workload, dom) in NCU_TRAFFIC else None,
+                "launches_per_step": 2 if dom.startswith("count") and args.workload == "cfg2" else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
                 "forward_backward": {"achieved": kernels["block_kernel (forward-backward)"]["gbs"],
                                      "frac": kernels["block_kernel (forward-backward)"]["gbs"] / peak_gbs,
