@@ -451,10 +451,18 @@ static bool pick_cfg(uint32_t P, TileCfg& c) {
   return false;
 }
 
-// PG_BLOCK_MINB=1 selects the un-capped-register variant of the (4,17,1) block kernel (tuning knob)
-static bool minb1() {
-  static const bool v = [] { const char* e = getenv("PG_BLOCK_MINB"); return e && e[0] == '1'; }();
-  return v;
+// Resident CTAs per SM the block kernel is compiled for (register cap = 64K / (MINB * NT)).  PG_BLOCK_MINB overrides
+// the default (tuning knob); every variant computes the same thing.
+static int block_minb(int NT) {
+  static const int env = [] { const char* e = getenv("PG_BLOCK_MINB"); return e ? atoi(e) : 0; }();
+  if (env >= 1 && env <= 4) return env;
+  return NT <= 160 ? 3 : NT <= 288 ? 2 : 1;  // measured: H=32 blocks 0.91 -> 0.74 ms at 3 CTAs/SM; H=64 spills at 3
+}
+
+template <int L, int CPL, int RPW, int NT, int MINB>
+static cudaError_t launch_block(const ChainParams& p, int grid_blocks, cudaStream_t s) {
+  block_kernel<L, CPL, RPW, NT, MINB><<<grid_blocks, NT, sizeof(ChainSmem), s>>>(p);
+  return cudaGetLastError();
 }
 
 template <int L, int CPL, int RPW, int NT>
@@ -462,8 +470,13 @@ static cudaError_t launch_pair(const ChainParams& p, uint32_t n_chrom, int grid_
   const size_t smem = sizeof(ChainSmem);
   if (skeleton) skeleton_kernel<L, CPL, RPW, NT><<<dim3(n_chrom, 2), NT, smem, s>>>(p);
   if (blocks) {
-    if (NT == 288 && minb1()) block_kernel<L, CPL, RPW, NT, 1><<<grid_blocks, NT, smem, s>>>(p);
-    else block_kernel<L, CPL, RPW, NT><<<grid_blocks, NT, smem, s>>>(p);
+    if (NT > 288) return launch_block<L, CPL, RPW, NT, 1>(p, grid_blocks, s);
+    switch (block_minb(NT)) {
+      case 1: return launch_block<L, CPL, RPW, NT, 1>(p, grid_blocks, s);
+      case 3: return launch_block<L, CPL, RPW, NT, (NT <= 288 ? 3 : 1)>(p, grid_blocks, s);
+      case 4: return launch_block<L, CPL, RPW, NT, (NT <= 160 ? 4 : NT <= 288 ? 3 : 1)>(p, grid_blocks, s);
+      default: return launch_block<L, CPL, RPW, NT, (NT <= 288 ? 2 : 1)>(p, grid_blocks, s);
+    }
   }
   return cudaGetLastError();
 }
@@ -471,8 +484,16 @@ static cudaError_t launch_pair(const ChainParams& p, uint32_t n_chrom, int grid_
 template <int L, int CPL, int RPW, int NT>
 static int occupancy_of() {
   int n = 0;
-  if (NT == 288 && minb1()) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, 1>, NT, sizeof(ChainSmem));
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT>, NT, sizeof(ChainSmem));
+  if (NT > 288) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, 1>, NT, sizeof(ChainSmem));
+    return n;
+  }
+  switch (block_minb(NT)) {
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, 1>, NT, sizeof(ChainSmem)); break;
+    case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, (NT <= 288 ? 3 : 1)>, NT, sizeof(ChainSmem)); break;
+    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, (NT <= 160 ? 4 : NT <= 288 ? 3 : 1)>, NT, sizeof(ChainSmem)); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, block_kernel<L, CPL, RPW, NT, (NT <= 288 ? 2 : 1)>, NT, sizeof(ChainSmem));
+  }
   return n;
 }
 

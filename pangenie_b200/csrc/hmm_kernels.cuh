@@ -367,21 +367,38 @@ struct Chain {
   }
 
   // ---- posterior writer for a fast-A column whose class sums sit in wr[wbuf] (call after the barrier) ----
-  // One warp: lane (alpha, beta) = (lane/4, lane%4) sums wr[beta][i] over rows i with allele index alpha.
+  // One warp folds the rows: M[alpha][beta] = sum over rows i with allele index alpha of wr[beta][i].  The writer sits on
+  // the critical path of its column (everyone meets it at the next barrier), so all 32 lanes share the row loop:
+  // biallelic columns use 8 lanes per (alpha, beta), columns with 3-4 alleles 2 lanes per (alpha, beta).
   __device__ __forceinline__ void write_posterior(int slot, int wbuf) {
     const double* d = desc_d(slot);
     const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
     if (A > HMM_FAST_A) return;
-    const uint32_t alpha = lane >> 2, beta = lane & 3;
+    if (A <= 2) {
+      const uint32_t combo = lane >> 3, sub = lane & 7, alpha = combo >> 1, beta = combo & 1;
+      double m = 0.0;
+      for (int i = (int)sub; i < P; i += 8) m += (sm->wr_ai[wbuf][i] == alpha) ? sm->wr[wbuf][beta][i] : 0.0;
+      m += __shfl_xor_sync(0xffffffffu, m, 1);
+      m += __shfl_xor_sync(0xffffffffu, m, 2);
+      m += __shfl_xor_sync(0xffffffffu, m, 4);
+      const double mt = __shfl_sync(0xffffffffu, m, (int)(((beta << 1) | alpha) << 3));  // M[beta][alpha]
+      if (sub == 0 && alpha <= beta && beta < A) {
+        const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
+        const uint16_t* ids = prm->allele_ids + prm->allele_off[v];
+        prm->post[prm->gl_off[v] + pair_index(ids[alpha], ids[beta])] = alpha == beta ? m : m + mt;
+      }
+      return;
+    }
+    const uint32_t half = lane >> 4, combo = lane & 15, alpha = combo >> 2, beta = combo & 3;
     double m = 0.0;
-    if (lane < 16 && alpha < A && beta < A)
-      for (int i = 0; i < P; ++i) m += (sm->wr_ai[wbuf][i] == alpha) ? sm->wr[wbuf][beta][i] : 0.0;
-    const double mt = __shfl_sync(0xffffffffu, m, (beta << 2) | alpha);  // M[beta][alpha]
-    if (lane < 16 && alpha <= beta && beta < A) {
+    if (alpha < A && beta < A)
+      for (int i = (int)half; i < P; i += 2) m += (sm->wr_ai[wbuf][i] == alpha) ? sm->wr[wbuf][beta][i] : 0.0;
+    m += __shfl_xor_sync(0xffffffffu, m, 16);
+    const double mt = __shfl_sync(0xffffffffu, m, (int)((beta << 2) | alpha));  // M[beta][alpha]
+    if (half == 0 && alpha <= beta && beta < A) {
       const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
       const uint16_t* ids = prm->allele_ids + prm->allele_off[v];
-      const double val = alpha == beta ? m : m + mt;
-      prm->post[prm->gl_off[v] + pair_index(ids[alpha], ids[beta])] = val;
+      prm->post[prm->gl_off[v] + pair_index(ids[alpha], ids[beta])] = alpha == beta ? m : m + mt;
     }
   }
 };
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
 // -------------------------------------------------------------------------------------------------
 // phase 2: block forward-backward with fused posterior.  Persistent CTAs pull (chromosome, block) jobs.
 // -------------------------------------------------------------------------------------------------
-template <int L, int CPL, int RPW, int NT, int MINB = (NT <= 288 ? 2 : 1)>
+template <int L, int CPL, int RPW, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) block_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);

@@ -1,1 +1,1 @@
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"block_kernel|skeleton_kernel" -s 3 -c 2 -o gpurun_out/prof_h64 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload h64s > gpurun_out/ncu_h64.out 2>&1; tail -2 gpurun_out/ncu_h64.out
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider 2>&1 | tail -15

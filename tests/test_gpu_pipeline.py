@@ -79,3 +79,30 @@ def test_resident_engine_reuses_the_panel_across_samples(engine, oracle):
     engine.run_resident(reads_d, segs_d, k=wl.k, **sub)
     for i, (g, w) in enumerate(zip(engine.fetch(), want_sub)):
         assert_results_close(g, w, label=f"subset, chromosome {i}")
+
+
+def test_configs1_full_size_properties(engine, monkeypatch):
+    """BASELINE.json configs[1] at full size (1 chromosome, 10k variants, 8 haplotypes, 10x reads) through
+    size-independent properties: the resident and the host-buffer paths agree bit for bit, the partitioned and the direct
+    counting paths produce identical counts, rows are normalised, the run is reproducible, the sample is recovered."""
+    import torch
+    wl = synth.make_workload(n_chrom=1, n_variants=10_000, n_haplotypes=8, coverage=10.0, seed=20260926)
+    kw = dict(recombrate=1.26, effective_N=1e-5)
+    got, peak = engine.genotype_run(wl.reads_fastq, wl.segments_fasta, wl.panels, k=wl.k, **kw)
+    lik = got[0].likelihoods.copy(); gt = got[0].genotype.copy(); gq = got[0].quality.copy()
+    counts = wl.panels[0].kmer_counts.copy(); cov = wl.panels[0].coverage.copy()
+    assert 5 <= peak <= 10                                           # ~7.5 expected (SURVEY 8d)
+    sums = np.add.reduceat(lik, got[0].gl_offsets[:-1].astype(np.int64))
+    assert np.allclose(sums[got[0].is_column == 1], 1.0, atol=1e-9)
+    t = np.sort(wl.truth[0].astype(np.int16), axis=1)
+    assert (gt.reshape(-1, 2) == t).all(axis=1).mean() > 0.9
+    # resident path (device text), direct and partitioned counting
+    reads_d = torch.from_numpy(wl.reads_fastq).cuda(); segs_d = torch.from_numpy(wl.segments_fasta).cuda()
+    for part_kb in ("0", "16384"):
+        monkeypatch.setenv("PG_COUNT_PART_KB", part_kb)
+        engine.load(wl.panels)
+        assert engine.run_resident(reads_d, segs_d, k=wl.k, **kw) == peak
+        res = engine.fetch()[0]
+        assert np.array_equal(wl.panels[0].kmer_counts, counts) and np.array_equal(wl.panels[0].coverage, cov)
+        assert np.array_equal(res.likelihoods, lik) and np.array_equal(res.genotype, gt) and np.array_equal(res.quality, gq)
+    assert engine.timings()["hmm_scan_used"] == 1
