@@ -298,7 +298,7 @@ struct TableRef {
 // Lookups whose home bucket is full of other keys (~8% at load 0.6) continue in the next bucket.  Doing that inside the
 // batched probe makes every warp execute the walk for a handful of lanes; instead they are parked in a shared-memory
 // queue and worked off afterwards with all lanes busy (drain_walks).
-constexpr uint32_t WQ_CAP = 768;
+constexpr uint32_t WQ_CAP = 1536;
 struct WalkQueue {
   uint32_t n;
   uint32_t pad;
@@ -673,7 +673,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 
 // Works through the partition buffers in partition order (persistent CTAs pulling items of PP_ITEM k-mers), so the
 // CTAs running at any moment hit one or two adjacent slices of the table.
-constexpr int PP_ITEM = 4096;
+constexpr int PP_ITEM = 8192;
 template <int OP>
 __global__ void __launch_bounds__(256, 3) probe_parts_kernel(const PartArgs pa, const TableRef T) {
   __shared__ uint32_t s_start[MAX_PARTS + 2];  // first item of each partition
@@ -705,6 +705,13 @@ __global__ void __launch_bounds__(256, 3) probe_parts_kernel(const PartArgs pa, 
     const uint32_t off = (item - s_start[q]) * PP_ITEM;
     const uint64_t* src = pa.buf + (size_t)q * pa.region_cap + off;
     const uint32_t m = min((uint32_t)PP_ITEM, nq - off);
+    // the k-mer stream comes from HBM: the next round's four k-mers are requested before the current round is probed
+    uint64_t nx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t j = (uint32_t)i * 256 + (uint32_t)tid;
+      nx[i] = j < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
+    }
 #pragma unroll 1
     for (uint32_t r = 0; r < m; r += 4 * 256) {
       uint64_t cn[4];
@@ -712,9 +719,10 @@ __global__ void __launch_bounds__(256, 3) probe_parts_kernel(const PartArgs pa, 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t j = r + (uint32_t)i * 256 + (uint32_t)tid;
-        const bool v = j < m;
-        cn[i] = v ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
-        vm |= v ? 1u << i : 0u;
+        cn[i] = nx[i];
+        vm |= j < m ? 1u << i : 0u;
+        const uint32_t jn = j + 4 * 256;
+        nx[i] = jn < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + jn)) : 0ull;
       }
       probe4<OP, true>(cn, vm, T, inserted, &s_wq);
     }

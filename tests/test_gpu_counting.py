@@ -127,3 +127,42 @@ def test_unsupported_inputs_fail_loudly():
     with pytest.raises(pg.PgError):
         rng = np.random.default_rng(1)
         pg.KmerCounter(synth._fasta_record("a", rng.integers(0, 4, size=40_000).astype(np.uint8)), None, 11, hash_size=10)  # count-all table too small
+
+
+def _random_text(rng, fastq: bool):
+    """Random FASTA/FASTQ with ragged line lengths, empty records, lower case, N / IUPAC / CR bytes."""
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTacgtNRYKM\r", np.uint8)
+    out = bytearray()
+    for r in range(int(rng.integers(1, 40))):
+        n = int(rng.choice([0, 1, 5, 6, 7, 8, 15, 16, 17, 31, 64, 100, 250, 4000, 9000]))
+        seq = alphabet[rng.integers(0, len(alphabet), size=n)].tobytes()
+        if fastq:
+            qual = bytes(rng.integers(33, 75, size=n, dtype=np.uint8))  # includes '@', '+', '>'
+            out += b"@r%d some text\n" % r + seq + b"\n+" + (b"r%d" % r if rng.random() < 0.3 else b"") + b"\n" + qual + b"\n"
+        else:
+            out += b">rec%d\n" % r
+            width = int(rng.choice([1, 7, 16, 60, 61, 4096, 100000]))
+            for i in range(0, n, width):
+                out += seq[i:i + width] + b"\n"
+                if rng.random() < 0.05:
+                    out += b"\n"  # empty line inside a record
+    if rng.random() < 0.3 and not fastq and out.endswith(b"\n"):
+        out = out[:-1]  # no trailing newline
+    return bytes(out)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzzed_formats_match_oracle(oracle, seed):
+    """Ragged random FASTA / FASTQ (empty records, lines of 1..100000 bases, IUPAC codes, CR bytes, '@' / '>' in quality
+    strings): every 7-mer count and the histogram agree with the CPU restatement, in all three counting modes."""
+    rng = np.random.default_rng(900 + seed)
+    all7 = np.arange(4 ** 7, dtype=np.uint64)
+    segs = _random_text(np.random.default_rng(77), False)
+    for trial in range(6):
+        text = _random_text(rng, fastq=bool(trial & 1))
+        for s in (None, segs):
+            g = pg.KmerCounter(text, s, 7, hash_size=40_000)
+            o = oracles.OracleCounter(oracle, text, s, 7)
+            assert np.array_equal(g.lookup(all7), o.lookup(all7)), (seed, trial, s is None)
+            assert np.array_equal(g.histogram(200), o.histogram(200))
+            assert g.distinct() == o.distinct()

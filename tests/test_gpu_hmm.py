@@ -214,3 +214,18 @@ def test_reference_catch_suite_passes_over_the_gpu_library():
     # every assertion but the Viterbi haplotype one (HMMTest.cpp:438, phasing is out of scope)
     assert " 1 failed" in tail[-1] and "HMMTest.cpp:438" in out, out[-3000:]
     assert out.count("FAILED:") == 1
+
+
+@pytest.mark.parametrize("n_paths", [1, 2, 3, 8, 9, 10, 16, 17, 20, 21, 36, 37, 68, 69, 136, 137, 256])
+def test_path_counts_at_kernel_configuration_boundaries(engine, oracle, n_paths):
+    """Every tile configuration of the chain kernels at its smallest and largest path count (csrc/genotype.cu pick_cfg),
+    several checkpoint blocks each, multi-allelic and undefined alleles included."""
+    rng = np.random.default_rng(4000 + n_paths)
+    n_var = 150 if n_paths <= 40 else 80 if n_paths <= 140 else 20
+    panel = random_panel(rng, n_var, n_paths, max_alleles=min(5, n_paths + 1), undefined_frac=0.1, ref_only_frac=0.02)
+    table = _table()
+    for normalize in (True, False):
+        kw = dict(recombrate=1.26, effective_N=25000.0 if n_paths % 2 else 1e-5, normalize=normalize)
+        want = oracles.cpu_hmm_run(oracle, "pgo_", [panel], table, **kw)[0]
+        got = engine.hmm_run([panel], table, **kw)[0]
+        assert_results_close(got, want, atol=1e-300, label=f"P={n_paths} normalize={normalize}")
