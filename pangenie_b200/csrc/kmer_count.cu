@@ -867,7 +867,8 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
 }
 
 // ---- partitioned counting: geometry and the probe pass over the filled buffers ----
-constexpr uint64_t SUPER_BYTES = 1ull << 30;  // text bytes scattered before the partition buffers are worked off
+// text bytes scattered before the partition buffers are worked off (PG_COUNT_SUPER_MB: test knob)
+static uint64_t super_bytes() { return std::max<uint64_t>(env_u64("PG_COUNT_SUPER_MB", 1024), 1) << 20; }
 // tuning / test knobs: PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
 // PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning
 static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 96u << 10) << 10; }
@@ -881,7 +882,7 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, PartAr
   const uint64_t table_bytes = (c->capacity >> 2) * sizeof(KmerBucket);
   if (op == PG_OP_PRIME || slice == 0 || table_bytes <= 2 * slice || len < env_u64("PG_COUNT_PART_MIN_TEXT", 4u << 20)) return PG_OK;
   const uint32_t n_parts = (uint32_t)std::min<uint64_t>(MAX_PARTS, (table_bytes + slice - 1) / slice);
-  const uint64_t super = std::min<uint64_t>(len, SUPER_BYTES);
+  const uint64_t super = std::min<uint64_t>(len, super_bytes());
   // every text byte starts at most one k-mer; 1.5x the mean share per partition, the excess is probed directly
   const uint64_t region = ((super + super / 2) / n_parts + 8192) & ~(uint64_t)15;
   const uint64_t need = region * n_parts;
@@ -946,11 +947,12 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   PG_CUDA(cudaEventRecord(ev0, c->stream));
   const bool direct = on_device && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   if (!direct && len) PG_TRY(ensure_stage(c, !on_device && !pinned));
-  const uint64_t step = direct ? CHUNK_BYTES : STAGE_BYTES;
+  uint64_t step = direct ? CHUNK_BYTES : STAGE_BYTES;
   PartArgs pa;
   memset(&pa, 0, sizeof(pa));
   bool parted = false;
   PG_TRY(part_setup(c, len, op, direct, pa, parted));
+  if (parted) step = std::min<uint64_t>(step, super_bytes());  // a chunk never exceeds what the regions are sized for
   if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, 256 * sizeof(uint32_t), c->stream));
   uint64_t scattered = 0;  // text bytes scattered into the partition buffers since the last flush
   for (uint64_t off = 0; off < len; off += step) {
@@ -982,7 +984,7 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
     if (after_first_chunk && off == 0) PG_TRY((*after_first_chunk)());  // host work that overlaps the copies in flight
     if (parted) {
       scattered += n;
-      if (off + step >= len || scattered + step > SUPER_BYTES) {  // buffers sized for SUPER_BYTES of text
+      if (off + step >= len || scattered + step > super_bytes()) {  // the buffers are sized for super_bytes() of text
         PG_TRY(part_flush(c, pa, op));
         scattered = 0;
       }

@@ -111,6 +111,10 @@ def test_partitioned_counting_matches_oracle(oracle, monkeypatch, part_kb):
     probes = np.concatenate([np.concatenate([p.kmer_codes for p in wl.panels])[:5000], _codes(rng, 2000, 31)])
     _compare(oracle, wl.reads_fastq, wl.segments_fasta, 31, probes)      # PRIME + UPDATE
     _compare(oracle, wl.reads_fastq[:400_000 // wl.record_bytes * wl.record_bytes], None, 31, probes)  # count-all (inserting) mode
+    # several super-chunks: the partition buffers are filled and worked off more than once per pass
+    monkeypatch.setenv("PG_COUNT_SUPER_MB", "1")
+    _compare(oracle, wl.reads_fastq, wl.segments_fasta, 31, probes)
+    monkeypatch.delenv("PG_COUNT_SUPER_MB")
     # skew: one k-mer dominates, its partition region overflows and the excess is probed directly
     poly = b"".join(b"@r%d\n" % i + b"A" * 150 + b"\n+\n" + b"F" * 150 + b"\n" for i in range(3000))
     text = poly + bytes(wl.reads_fastq[:200 * wl.record_bytes])
