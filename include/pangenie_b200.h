@@ -222,6 +222,17 @@ void pg_engine_destroy(pg_engine* e);
 int pg_hmm_run(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
                const pg_hmm_params* params, pg_hmm_result* results);
 
+/**
+ * Genotyping over several subsets of paths — the `-a` mode of the reference (src/commands.cpp:916-993): every subset is
+ * run like `HMM(..., normalize = false, only_paths = subset)` (run_genotyping, :155-160), the likelihoods are added per
+ * variant (`GenotypingResult::combine`, :166-176) and normalised once at the end (:982-988).  subset k uses the path ids
+ * subset_paths[subset_offsets[k] .. subset_offsets[k+1]).  The partition of the paths itself (PathSampler) stays with the
+ * caller.  Results as for pg_hmm_run with normalize = 1; `is_column` is the union over the subsets.
+ */
+int pg_hmm_run_subsets(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
+                       const pg_hmm_params* params, uint32_t n_subsets, const uint32_t* subset_offsets,
+                       const uint16_t* subset_paths, pg_hmm_result* results);
+
 /** Emission tables only — `EmissionProbabilityComputer` (src/emissionprobabilitycomputer.cpp:9-34).
  *  emissions: for variant v a dense (maxA+1)x(maxA+1) row-major matrix at em_offsets[v] (maxA = largest
  *  allele id), entries for allele pairs not in the variant's allele map are 0; values are scaled by

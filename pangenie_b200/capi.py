@@ -113,7 +113,7 @@ EXPORTS = [
     "pg_result_layout", "pg_engine_create", "pg_engine_destroy", "pg_hmm_run", "pg_emission_run",
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
     "pg_count_device_arrays", "pg_count_export_counts", "pg_count_import_counts", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
-    "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted",
+    "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted", "pg_hmm_run_subsets",
 ]
 
 
@@ -174,6 +174,8 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "engine_destroy", None, [vp])
         _sig(lib, p + "engine_timings", i32, [vp, C.POINTER(PgTimings)])
         _sig(lib, p + "hmm_run", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgProbTable), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult)])
+        _sig(lib, p + "hmm_run_subsets", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgProbTable), C.POINTER(PgHmmParams), u32, vp, vp,
+                                                 C.POINTER(PgHmmResult)])
         _sig(lib, p + "emission_run", i32, [vp, C.POINTER(PgPanel), C.POINTER(PgProbTable), vp, vp, vp])
         _sig(lib, p + "fill_counts", i32, [vp, vp, u64, u32, C.POINTER(PgPanel)])
         _sig(lib, p + "engine_load", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgHmmResult)])

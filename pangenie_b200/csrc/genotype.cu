@@ -304,6 +304,11 @@ struct FinalizeArgs {
   uint16_t* coverage_out;
   int normalize;
   uint32_t P;
+  // subset combination (run_genotyping, src/commands.cpp:166-176): mode 1 adds the reference-scale likelihoods of this
+  // subset to `acc` and ORs the column flags into `col_any` instead of writing results
+  int mode;
+  double* acc;
+  uint8_t* col_any;
 };
 
 __device__ __forceinline__ double log_pow2_scale(double T) { return log(pow2_scale_of(T)); }
@@ -423,7 +428,13 @@ __global__ void __launch_bounds__(128) finalize_kernel(FinalizeArgs a) {
       }
     }
     const double fac = exp(logfac);
-    for (uint32_t g = 0; g < n; ++g) L[g] *= fac;
+    if (a.mode == 1) {
+      double* acc = a.acc + a.gl_off[v];
+      for (uint32_t g = 0; g < n; ++g) acc[g] += L[g] * fac;  // GenotypingResult::combine (genotypingresult.cpp:193-198)
+      a.col_any[v] = 1;
+    } else {
+      for (uint32_t g = 0; g < n; ++g) L[g] *= fac;
+    }
   }
 }
 
@@ -523,8 +534,8 @@ struct pg_engine {
   bool has_codes = false;
   uint64_t GL = 0, EM = 0;
   // scratch
-  DevBuf<double> log_p, em, log_scale, ckpt_fwd, ckpt_bwd, tot_fwd, tot_bwd, block_buf, post;
-  DevBuf<uint8_t> is_column, desc;
+  DevBuf<double> log_p, em, log_scale, ckpt_fwd, ckpt_bwd, tot_fwd, tot_bwd, block_buf, post, post_acc;
+  DevBuf<uint8_t> is_column, desc, col_any;
   DevBuf<uint16_t> sel, unique_kmers, coverage_out;
   DevBuf<uint32_t> col_variant, col_cbeg, col_cend, variant_col, work_counter, quality;
   DevBuf<int16_t> genotype;
@@ -607,6 +618,7 @@ extern "C" void pg_engine_destroy(pg_engine* e) {
     e->unique_kmers.release(); e->coverage_out.release(); e->col_variant.release(); e->col_cbeg.release();
     e->col_cend.release(); e->variant_col.release(); e->work_counter.release(); e->quality.release();
     e->genotype.release(); e->chroms.release(); e->jobs.release();
+    e->post_acc.release(); e->col_any.release();
     e->tjobs.release(); e->scan_chroms.release(); e->scan_mats.release(); e->seq_flags.release();
   }
   delete e;
@@ -787,7 +799,7 @@ static int run_emission(pg_engine* e, const TableDev& td) {
 }
 
 // ---- forward-backward over the loaded panel (counts + coverage resident) -------------------------------
-static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_params* prm) {
+static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_params* prm, int fin_mode = 0) {
   DeviceGuard g(e->device);
   cudaStream_t s = e->stream;
   const uint32_t V = e->V, Pfull = e->P;
@@ -1049,6 +1061,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     fa.kmer_off = e->kmer_off.p; fa.coverage = e->coverage.p; fa.post = e->post.p; fa.genotype = e->genotype.p;
     fa.quality = e->quality.p; fa.unique_kmers = e->unique_kmers.p; fa.coverage_out = e->coverage_out.p;
     fa.normalize = prm->normalize; fa.P = P;
+    fa.mode = fin_mode; fa.acc = e->post_acc.p; fa.col_any = e->col_any.p;
     const int grid = (int)std::min<uint64_t>(((uint64_t)V + 127) / 128, (uint64_t)e->sm_count * 16);
     finalize_kernel<<<grid, 128, 0, s>>>(fa);
     count_launch();
@@ -1156,6 +1169,68 @@ extern "C" int pg_hmm_run(pg_engine* e, uint32_t n_chrom, const pg_panel* panels
   memset(&e->tm, 0, sizeof(e->tm));
   PG_TRY(engine_load_panels(e, n_chrom, panels, results, true, false));
   PG_TRY(engine_hmm(e, table, params));
+  PG_TRY(engine_fetch_results(e, n_chrom, panels, results));
+  e->tm.kernel_launches = g_launches - l0;
+  return PG_OK;
+}
+
+// Genotyping over several path subsets (`-a`, src/commands.cpp:916-993): every subset is run un-normalised, the
+// likelihoods are added up (run_genotyping, :166-176) and normalised at the end (:982-988); GT / GQ follow from the sum.
+static int engine_hmm_subsets(pg_engine* e, const pg_probtable* table, const pg_hmm_params* prm, uint32_t n_subsets,
+                              const uint32_t* subset_offsets, const uint16_t* subset_paths) {
+  DeviceGuard g(e->device);
+  cudaStream_t s = e->stream;
+  const uint32_t V = e->V;
+  PG_TRY(e->post_acc.reserve(std::max<uint64_t>(e->GL, 1)));
+  PG_TRY(e->col_any.reserve(std::max<uint32_t>(V, 1)));
+  PG_CUDA(cudaMemsetAsync(e->post_acc.p, 0, std::max<uint64_t>(e->GL, 1) * 8, s));
+  PG_CUDA(cudaMemsetAsync(e->col_any.p, 0, std::max<uint32_t>(V, 1), s));
+  pg_timings acc_tm;
+  memset(&acc_tm, 0, sizeof(acc_tm));
+  for (uint32_t k = 0; k < n_subsets; ++k) {
+    pg_hmm_params ps = *prm;
+    ps.only_paths = subset_paths + subset_offsets[k];
+    ps.n_only_paths = subset_offsets[k + 1] - subset_offsets[k];
+    ps.normalize = 0;
+    PG_TRY(engine_hmm(e, table, &ps, 1));
+    acc_tm.emission_ms += e->tm.emission_ms; acc_tm.hmm_skeleton_ms += e->tm.hmm_skeleton_ms;
+    acc_tm.hmm_blocks_ms += e->tm.hmm_blocks_ms; acc_tm.finalize_ms += e->tm.finalize_ms;
+    acc_tm.hmm_columns += e->tm.hmm_columns; acc_tm.hmm_block_launches += e->tm.hmm_block_launches;
+  }
+  if (V) {
+    // the sum becomes the result: normalise, genotype and quality as for a single run
+    PG_CUDA(cudaMemcpyAsync(e->post.p, e->post_acc.p, std::max<uint64_t>(e->GL, 1) * 8, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA(cudaMemcpyAsync(e->is_column.p, e->col_any.p, V, cudaMemcpyDeviceToDevice, s));
+    FinalizeArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.V = V; fa.is_column = e->is_column.p; fa.gl_off = e->gl_off.p; fa.allele_off = e->allele_off.p;
+    fa.allele_ids = e->allele_ids.p; fa.allele_undef = e->allele_undef.p; fa.kmer_off = e->kmer_off.p;
+    fa.coverage = e->coverage.p; fa.post = e->post.p; fa.genotype = e->genotype.p; fa.quality = e->quality.p;
+    fa.unique_kmers = e->unique_kmers.p; fa.coverage_out = e->coverage_out.p;
+    fa.normalize = 1;  // the normalised branch reads none of the per-column arrays
+    const int grid = (int)std::min<uint64_t>(((uint64_t)V + 127) / 128, (uint64_t)e->sm_count * 16);
+    finalize_kernel<<<grid, 128, 0, s>>>(fa);
+    count_launch();
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaStreamSynchronize(s));
+  }
+  e->cols.valid = false;  // is_column now holds the union over the subsets, not the last subset's columns
+  e->tm.emission_ms = acc_tm.emission_ms; e->tm.hmm_skeleton_ms = acc_tm.hmm_skeleton_ms;
+  e->tm.hmm_blocks_ms = acc_tm.hmm_blocks_ms; e->tm.finalize_ms = acc_tm.finalize_ms;
+  e->tm.hmm_columns = acc_tm.hmm_columns; e->tm.hmm_block_launches = acc_tm.hmm_block_launches;
+  return PG_OK;
+}
+
+extern "C" int pg_hmm_run_subsets(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
+                                  const pg_hmm_params* params, uint32_t n_subsets, const uint32_t* subset_offsets,
+                                  const uint16_t* subset_paths, pg_hmm_result* results) {
+  clear_error();
+  if (!e || !panels || !table || !params || !results || !subset_offsets || !subset_paths || n_subsets == 0)
+    return fail(PG_ERR_ARG, "null argument");
+  const uint64_t l0 = g_launches;
+  memset(&e->tm, 0, sizeof(e->tm));
+  PG_TRY(engine_load_panels(e, n_chrom, panels, results, true, false));
+  PG_TRY(engine_hmm_subsets(e, table, params, n_subsets, subset_offsets, subset_paths));
   PG_TRY(engine_fetch_results(e, n_chrom, panels, results));
   e->tm.kernel_launches = g_launches - l0;
   return PG_OK;

@@ -212,6 +212,23 @@ class Engine:
         _check(self._lib, self._lib.pg_hmm_run(self._h, len(panels), pa, C.byref(table.t), C.byref(prm), ra))
         return results
 
+    def hmm_run_subsets(self, panels, table: ProbabilityTable, subsets, results=None, **kw):
+        """The reference's `-a` mode (src/commands.cpp:916-993): one un-normalised run per path subset, likelihoods added
+        per variant (run_genotyping, :166-176), normalised at the end.  `subsets` = list of lists of path ids."""
+        if results is None:
+            results = [Result(p) for p in panels]
+        prm, _keep = hmm_params(**kw)
+        off = np.zeros(len(subsets) + 1, np.uint32)
+        off[1:] = np.cumsum([len(x) for x in subsets])
+        paths = np.ascontiguousarray(np.concatenate([np.asarray(x, np.uint16) for x in subsets]))
+        pa = self._panel_array(panels)
+        ra = (PgHmmResult * len(panels))()
+        for i, r in enumerate(results):
+            ra[i] = r.as_struct()
+        _check(self._lib, self._lib.pg_hmm_run_subsets(self._h, len(panels), pa, C.byref(table.t), C.byref(prm), len(subsets),
+                                                        ptr(off), ptr(paths), ra))
+        return results
+
     def emission_run(self, panel: Panel, table: ProbabilityTable):
         """EmissionProbabilityComputer for every variant -> (offsets, dense (maxA+1)^2 matrices, log_scale)."""
         V = panel.n_variants

@@ -142,6 +142,35 @@ def test_hmm_options(engine, oracle):
         assert_results_close(got, want, label=str(kw))
 
 
+def test_path_subsets_are_combined_like_the_reference(engine, oracle):
+    """`-a`: run_genotyping adds the un-normalised likelihoods of disjoint path subsets and normalises at the end
+    (src/commands.cpp:155-176, 982-988).  Expected values: the oracle run per subset with normalize=False, summed."""
+    rng = np.random.default_rng(17)
+    panels = [random_panel(rng, n, 12, max_alleles=3, undefined_frac=0.05, ref_only_frac=0.05) for n in (260, 90)]
+    table = _table()
+    subsets = [[0, 4, 7, 9], [1, 2, 3, 11], [5, 6, 8, 10]]
+    kw = dict(recombrate=1.26, effective_N=25000.0)
+    got = engine.hmm_run_subsets(panels, table, subsets, **kw)
+    for c, panel in enumerate(panels):
+        total = None
+        col_any = np.zeros(panel.n_variants, bool)
+        for sub in subsets:
+            r = oracles.cpu_hmm_run(oracle, "pgo_", [panel], table, only_paths=sub, normalize=False, **kw)[0]
+            total = r.likelihoods.copy() if total is None else total + r.likelihoods
+            col_any |= r.is_column == 1
+        off = got[c].gl_offsets.astype(np.int64)
+        sums = np.add.reduceat(total, off[:-1])
+        norm = total / np.repeat(np.where(sums > 0, sums, 1.0), np.diff(off))
+        assert np.array_equal(got[c].is_column == 1, col_any)
+        np.testing.assert_allclose(got[c].likelihoods, norm, rtol=1e-6, atol=1e-300)
+        # GT = the likeliest genotype of the combined likelihoods (biallelic and defined variants checked by argmax)
+        for v in np.nonzero(col_any)[0][:200]:
+            row = norm[off[v]:off[v + 1]]
+            if len(row) == 3 and np.sort(row)[-1] - np.sort(row)[-2] > 1e-6 and not panel.allele_undefined[panel.allele_offsets[v]:panel.allele_offsets[v + 1]].any():
+                g = [(0, 0), (0, 1), (1, 1)][int(np.argmax(row))]
+                assert tuple(got[c].genotype[2 * v:2 * v + 2]) == g, v
+
+
 def test_hmm_matches_reference_sources_directly(engine, ref):
     rng = np.random.default_rng(11)
     panel = random_panel(rng, 120, 12, max_alleles=4, undefined_frac=0.15)
