@@ -674,7 +674,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 // Works through the partition buffers in partition order (persistent CTAs pulling items of PP_ITEM k-mers), so the
 // CTAs running at any moment hit one or two adjacent slices of the table.
 constexpr int PP_ITEM = 8192;
-constexpr int PP_BATCH = 8;  // k-mers per thread per round (measured: 2 -> 49.5 ms, 4 -> 42.8 ms on the cfg3s UPDATE pass)
+constexpr int PP_BATCH = 4;  // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
 template <int OP>
 __global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, const TableRef T) {
   __shared__ uint32_t s_start[MAX_PARTS + 2];  // first item of each partition
