@@ -897,8 +897,9 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   PG_TRY(e->desc.reserve(std::max<size_t>((size_t)C * stride, 16)));
   PG_TRY(e->tot_fwd.reserve(std::max<uint32_t>(C, 1)));
   PG_TRY(e->tot_bwd.reserve(std::max<uint32_t>(C, 1)));
-  PG_TRY(e->ckpt_fwd.reserve(std::max<size_t>((size_t)nblk * PP, 1)));
-  PG_TRY(e->ckpt_bwd.reserve(std::max<size_t>((size_t)nblk * PP, 1)));
+  const size_t CS = (size_t)P * P;  // doubles per checkpoint (dense)
+  PG_TRY(e->ckpt_fwd.reserve(std::max<size_t>((size_t)nblk * CS, 1)));
+  PG_TRY(e->ckpt_bwd.reserve(std::max<size_t>((size_t)nblk * CS, 1)));
   PG_TRY(e->work_counter.reserve(4));
   PG_TRY(e->genotype.reserve(std::max<uint32_t>(2 * V, 2)));
   PG_TRY(e->quality.reserve(std::max<uint32_t>(V, 1)));
@@ -930,6 +931,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
 
     ChainParams cp;
     cp.state_stride = (uint32_t)PP;
+    cp.ckpt_stride = (uint32_t)CS;
     cp.P = P; cp.B = B; cp.desc = e->desc.p; cp.desc_stride = stride; cp.chroms = e->chroms.p;
     cp.ckpt_fwd = e->ckpt_fwd.p; cp.ckpt_bwd = e->ckpt_bwd.p; cp.tot_fwd = e->tot_fwd.p; cp.tot_bwd = e->tot_bwd.p;
     cp.post = e->post.p; cp.gl_off = e->gl_off.p; cp.allele_off = e->allele_off.p; cp.allele_ids = e->allele_ids.p;

@@ -28,7 +28,7 @@ namespace pg {
 constexpr int HMM_PMAX = 256;       // largest number of selected paths supported
 constexpr int HMM_RS_PAD = 288;     // row-sum array length in shared memory
 constexpr int HMM_NSLOT = 8;        // descriptor ring slots (power of two: slot = column & 7)
-constexpr int HMM_PREFETCH = 4;     // descriptor prefetch distance (columns)
+constexpr int HMM_PREFETCH = 4;     // descriptor prefetch distance (columns); 8 columns + L2 hints measured no faster
 constexpr int HMM_FAST_A = 4;       // columns with <= 4 alleles: staged emission table + class sums
 constexpr int HMM_BMAX = 256;       // largest block length
 
@@ -61,7 +61,9 @@ struct ChainParams {
   double* tot_fwd;             // [n_cols] TF_t = sum F_t
   double* tot_bwd;             // [n_cols] TY_t = sum Y_t
   double* block_buf;           // [grid][B][state_stride] forward columns of the block being processed
-  uint32_t state_stride;       // doubles per stored state = cells per thread x threads (thread-major private layout)
+  uint32_t state_stride;       // doubles per stored block_buf column = cells per thread x threads (thread-major private layout)
+  uint32_t ckpt_stride;        // doubles per checkpoint = P*P: dense row-major, independent of the tile configuration, so the
+                               // skeleton may use a wider CTA than the block kernel (and the scan path writes the same format)
   double* post;                // VCF-ordered raw posteriors (zero-initialised)
   const uint64_t* gl_off;      // [n_variants+1]
   const uint32_t* allele_off;  // [n_variants+1]
@@ -203,6 +205,27 @@ struct Chain {
       const bool rok = row(r) < P;
 #pragma unroll
       for (int s = 0; s < CPL; ++s) x[r][s] = (rok && ((vmask >> s) & 1u)) ? src[(size_t)(r * CPL + s) * NT + threadIdx.x] : 0.0;
+    }
+  }
+  // checkpoints: dense row-major P x P (layout shared by every tile configuration and by hmm_scan.cuh)
+  __device__ __forceinline__ void store_dense(double* dst) const {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = row(r);
+      if (i < P) {
+#pragma unroll
+        for (int s = 0; s < CPL; ++s)
+          if ((vmask >> s) & 1u) dst[(size_t)i * P + col0 + s] = x[r][s];
+      }
+    }
+  }
+  __device__ __forceinline__ void load_dense(const double* src) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = row(r);
+      const bool rok = i < P;
+#pragma unroll
+      for (int s = 0; s < CPL; ++s) x[r][s] = (rok && ((vmask >> s) & 1u)) ? src[(size_t)i * P + col0 + s] : 0.0;
     }
   }
   // stored forward column -> registers (issued early so the latency overlaps the reductions of the step)
@@ -418,7 +441,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
   for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;  // zero padding beyond P
   ch.sync();
   const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
-  const size_t PP = p.state_stride;
+  const size_t CS = p.ckpt_stride;
   double nou[RPW][CPL];  // unused (no posterior in the skeleton); the compiler drops it
   constexpr int D = HMM_PREFETCH;
   int cur = 0;
@@ -442,7 +465,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
     uint32_t blk = cc.blk_begin + 1;
     for (int t = c0 + 1; t <= last; ++t) {
       if (until_ckpt == 0) {
-        ch.store_state(p.ckpt_fwd + (size_t)blk * PP);
+        ch.store_dense(p.ckpt_fwd + (size_t)blk * CS);
         ++blk;
         until_ckpt = B;
       }
@@ -456,7 +479,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
       slot = ch.slot_next(slot);
       cur ^= 1;
     }
-    ch.store_state(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * PP);
+    ch.store_dense(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * CS);
   } else {
     // backward: needs Y at columns c0 + k*B for k = 1 .. n_blocks-1 (stored as ckpt_bwd[k-1]).
     // The ring is walked downwards: slot(t-1) = slot(t) - 1 (mod NSLOT).
@@ -472,7 +495,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
     ch.template step<true, true, false>(slot, 0, 0, 0.0, nou, 0);
     int rel = (c1 - 1 - c0) % B;        // position of column t inside its block (one division per chain)
     uint32_t blk = cc.blk_begin + (uint32_t)((c1 - 1 - c0) / B);
-    if (rel == 0) ch.store_state(p.ckpt_bwd + (size_t)(blk - 1) * PP);
+    if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
     ch.prefetch_desc(c1 - 1 - D, c0, c1, pslot);
     pslot = slot_prev(pslot);
     cp_async_wait<D - 1>();
@@ -486,7 +509,7 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
       --rel;
       const double T = ch.total(cur);
       ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nou, 0);
-      if (rel == 0) ch.store_state(p.ckpt_bwd + (size_t)(blk - 1) * PP);
+      if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
       ch.prefetch_desc(t - D, c0, c1, pslot);
       pslot = slot_prev(pslot);
       cp_async_wait<D - 1>();
@@ -550,7 +573,7 @@ __global__ void __launch_bounds__(NT, MINB) block_kernel(const ChainParams p) {
       slot = ch.slot_next(slot);
       t = cb + 1;
     } else {
-      ch.load_state(p.ckpt_fwd + (size_t)gblk * PP);
+      ch.load_dense(p.ckpt_fwd + (size_t)gblk * p.ckpt_stride);
       ch.publish_rowsums(0);
       cp_async_wait<D - 1>();
       ch.sync();
@@ -604,7 +627,7 @@ __global__ void __launch_bounds__(NT, MINB) block_kernel(const ChainParams p) {
       slot = slot_prev(slot);
       --t;
     } else {
-      ch.load_state(p.ckpt_bwd + (size_t)gblk * PP);
+      ch.load_dense(p.ckpt_bwd + (size_t)gblk * p.ckpt_stride);
       ch.publish_rowsums(0);
       cp_async_wait<D - 1>();
       ch.sync();

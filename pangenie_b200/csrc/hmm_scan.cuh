@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(BASIS_WARPS * 32, 8) basis_kernel(const ChainP
 
 // -------------------------------------------------------------------------------------------------
 // 2. checkpoint scan.  grid = (n_chrom, 2): y = 0 forward, y = 1 backward; one upper-triangle cell per thread.
-//    Checkpoints are written in the thread-major layout of Chain<1, CPL, 1, 32> (cell (i,j) at [j*32 + i]).
+//    Checkpoints are dense row-major P x P (ChainParams::ckpt_stride), like those of skeleton_kernel.
 // -------------------------------------------------------------------------------------------------
 constexpr int SCAN_RING = 4;   // transfer matrices in flight (L2 -> shared memory), one cp.async group each
 constexpr int SCAN_SPLIT = 4;  // lanes sharing one cell: each sums a quarter of the basis range
@@ -313,9 +313,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ChainParams p,
     if (cell_ok && part == 0) {
       sm.st[cell] = v;  // read again only after the next barrier; the readers of this step passed the second one
       const uint32_t out_blk = dir ? sc.out_first[1] - q : sc.out_first[0] + q;
-      double* out = (dir ? p.ckpt_bwd : p.ckpt_fwd) + (size_t)out_blk * p.state_stride;
-      out[(size_t)cj * 32 + ci] = v;
-      if (ci != cj) out[(size_t)ci * 32 + cj] = v;
+      double* out = (dir ? p.ckpt_bwd : p.ckpt_fwd) + (size_t)out_blk * p.ckpt_stride;  // dense row-major P x P
+      out[(size_t)ci * P + cj] = v;
+      if (ci != cj) out[(size_t)cj * P + ci] = v;
     }
   }
   cp_async_wait<0>();
