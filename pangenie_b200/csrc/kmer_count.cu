@@ -230,27 +230,37 @@ __device__ __forceinline__ int block_exscan_max(int v, int* s_warp) {
 // Slow path of an INSERTING operation (PRIME / COUNT): `b` is the bucket to (re)examine, position by position with
 // FRESH reads (the snapshot taken by the fast path may be stale after a lost CAS).  On success `slot` = 4*bucket + pos.
 // Positions < j0 of the FIRST bucket are known to hold other keys (keys never change once set), so the walk starts at j0.
+// Every bucket is examined through ONE fresh 2 x 128-bit snapshot (ld.volatile semantics: the fast path's snapshot may be
+// stale after a lost CAS), then the first empty position is claimed; a lost CAS re-reads the same bucket behind it.
 template <int OP>
 __device__ __noinline__ bool resolve_insert(uint64_t kmer, uint64_t b, uint64_t& slot, KmerBucket* tab, uint64_t nb,
                                             unsigned long long* scalars, uint32_t& inserted, int j0 = 0) {
-  for (uint32_t probes = 0; probes < (1u << 20); ++probes, j0 = 0) {
-#pragma unroll 1
-    for (int j = j0; j < 4; ++j) {
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tab[b].key[j]);
-      if (cur == EMPTY_KEY) {
-        cur = atomicCAS(&tab[b].key[j], (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
-        if (cur == EMPTY_KEY) {
-          ++inserted;
-          slot = 4 * b + j;
-          return true;
-        }
-      }
-      if (cur == kmer) {
-        slot = 4 * b + j;
+  for (uint32_t probes = 0; probes < (1u << 22); ++probes) {
+    const ulonglong2 ka = __ldcv(reinterpret_cast<const ulonglong2*>(&tab[b].key[0]));
+    const ulonglong2 kb = __ldcv(reinterpret_cast<const ulonglong2*>(&tab[b].key[2]));
+    const unsigned long long k4[4] = {ka.x, ka.y, kb.x, kb.y};
+    int pos = -1, empty = 4;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      if (j >= j0 && k4[j] == kmer) pos = j;
+      if (j >= j0 && k4[j] == EMPTY_KEY) empty = j;
+    }
+    if (pos >= 0 && pos < empty) {
+      slot = 4 * b + pos;
+      return true;
+    }
+    if (empty < 4) {
+      const unsigned long long old = atomicCAS(&tab[b].key[empty], (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
+      if (old == EMPTY_KEY) ++inserted;
+      if (old == EMPTY_KEY || old == kmer) {
+        slot = 4 * b + empty;
         return true;
       }
+      j0 = empty + 1;  // lost the position to another key: look behind it
+      if (j0 < 4) continue;
     }
     b = b + 1 == nb ? 0 : b + 1;
+    j0 = 0;
   }
   atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);
   return false;
@@ -348,7 +358,9 @@ __device__ __forceinline__ void probeN(const uint64_t (&cn)[N], uint32_t vm, con
     ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
     kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
   }
-  uint32_t hitm = 0, need = 0;  // bit i: k-mer i found, its slot is in bkt[i] / continue in bucket bkt[i]
+  uint32_t hitm = 0, need = 0;  // bit i: k-mer i found, its slot is in bkt[i] / continue in bucket bkt[i] (UPDATE) or CAS pending
+  unsigned long long cas_old[N];
+  uint32_t cas_pos = 0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     if ((vm >> i) & 1u) {
@@ -375,16 +387,46 @@ __device__ __forceinline__ void probeN(const uint64_t (&cn)[N], uint32_t vm, con
             bkt[i] = nxt;
           }
         }
-      } else {
+      } else if (full) {
         uint64_t slot = 0;
-        // first empty position of the snapshot: everything before it is occupied by other keys
-        const int j0 = full ? 0 : (ka[i].x == EMPTY_KEY ? 0 : ka[i].y == EMPTY_KEY ? 1 : kb[i].x == EMPTY_KEY ? 2 : 3);
-        if (resolve_insert<OP>(kmer, full ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i], slot, tab, nbuckets, T.scalars, inserted, j0)) {
+        if (resolve_insert<OP>(kmer, bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1, slot, tab, nbuckets, T.scalars, inserted, 0)) {
           hitm |= 1u << i;
           bkt[i] = slot;
         }
+      } else {
+        // claim the first empty position of the snapshot (everything before it holds other keys); the CAS of all the
+        // k-mers of this round are in flight together, their outcome is examined below
+        const int j0 = ka[i].x == EMPTY_KEY ? 0 : ka[i].y == EMPTY_KEY ? 1 : kb[i].x == EMPTY_KEY ? 2 : 3;
+        cas_old[i] = atomicCAS(&tab[bkt[i]].key[j0], (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
+        cas_pos |= (uint32_t)j0 << (2 * i);
+        need |= 1u << i;
       }
     }
+  }
+  if (OP != PG_OP_UPDATE) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if ((need >> i) & 1u) {
+        const int j0 = (int)((cas_pos >> (2 * i)) & 3u);
+        const uint64_t kmer = cn[i];
+        if (cas_old[i] == EMPTY_KEY) {
+          ++inserted;
+          hitm |= 1u << i;
+          bkt[i] = 4 * bkt[i] + j0;
+        } else if (cas_old[i] == kmer) {  // another thread inserted the same k-mer first
+          hitm |= 1u << i;
+          bkt[i] = 4 * bkt[i] + j0;
+        } else {  // lost the position to a different key: continue behind it with fresh reads
+          uint64_t slot = 0;
+          const uint64_t b2 = j0 == 3 ? (bkt[i] + 1 == nbuckets ? 0 : bkt[i] + 1) : bkt[i];
+          if (resolve_insert<OP>(kmer, b2, slot, tab, nbuckets, T.scalars, inserted, j0 == 3 ? 0 : j0 + 1)) {
+            hitm |= 1u << i;
+            bkt[i] = slot;
+          }
+        }
+      }
+    }
+    need = 0;
   }
   if (OP == PG_OP_UPDATE && !USEQ) {
     // walk on in place, again with all pending loads of the thread in flight together
