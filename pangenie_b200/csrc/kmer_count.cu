@@ -305,6 +305,13 @@ struct TableRef {
   uint32_t flags;  // bit 0: plain atomics instead of warp-aggregated ones (experiment knob PG_COUNT_NOAGG)
 };
 
+// position of `kmer` among the four keys of a bucket snapshot, -1 if absent; branch-free (the short-circuit form compiles to
+// a ladder of divergent branches: the lanes of a warp match at different positions)
+__device__ __forceinline__ int match_pos(const ulonglong2& ka, const ulonglong2& kb, uint64_t kmer) {
+  const uint32_t m = (ka.x == kmer ? 1u : 0u) | (ka.y == kmer ? 2u : 0u) | (kb.x == kmer ? 4u : 0u) | (kb.y == kmer ? 8u : 0u);
+  return (int)__ffs(m) - 1;
+}
+
 // Lookups whose home bucket is full of other keys (~8% at load 0.6) continue in the next bucket.  Doing that inside the
 // batched probe makes every warp execute the walk for a handful of lanes; instead they are parked in a shared-memory
 // queue and worked off afterwards with all lanes busy (drain_walks).
@@ -321,7 +328,7 @@ __device__ __noinline__ void walk_count(uint64_t kmer, uint64_t b, const TableRe
   for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
     const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&T.tab[b].key[0]);
     const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&T.tab[b].key[2]);
-    const int pos = ka.x == kmer ? 0 : ka.y == kmer ? 1 : kb.x == kmer ? 2 : kb.y == kmer ? 3 : -1;
+    const int pos = match_pos(ka, kb, kmer);
     if (pos >= 0) {
       atomicAdd(&T.tab[b].cnt[pos], 1u);
       return;
@@ -366,7 +373,7 @@ __device__ __forceinline__ void probeN(const uint64_t (&cn)[N], uint32_t vm, con
     if ((vm >> i) & 1u) {
       // a match in the snapshot is definitive; so is a miss while the table is static (UPDATE)
       const uint64_t kmer = cn[i];
-      const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+      const int pos = match_pos(ka[i], kb[i], kmer);
       const bool full = kb[i].y != EMPTY_KEY;  // positions fill left to right
       if (pos >= 0) {
         hitm |= 1u << i;
@@ -442,7 +449,7 @@ __device__ __forceinline__ void probeN(const uint64_t (&cn)[N], uint32_t vm, con
       for (int i = 0; i < N; ++i)
         if ((need >> i) & 1u) {
           const uint64_t kmer = cn[i];
-          const int pos = ka[i].x == kmer ? 0 : ka[i].y == kmer ? 1 : kb[i].x == kmer ? 2 : kb[i].y == kmer ? 3 : -1;
+          const int pos = match_pos(ka[i], kb[i], kmer);
           if (pos >= 0) {
             hitm |= 1u << i;
             need &= ~(1u << i);
