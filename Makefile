@@ -4,16 +4,21 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xptxas -v
 CSRC := pangenie_b200/csrc
 LIB := pangenie_b200/libpangenie_b200.so
-SRCS := $(CSRC)/host_model.cu $(CSRC)/kmer_count.cu $(CSRC)/genotype.cu
+SRCS := $(CSRC)/host_model.cu $(CSRC)/kmer_count.cu $(CSRC)/genotype.cu $(CSRC)/index_io.cu
 HDRS := $(CSRC)/common.cuh $(CSRC)/hmm_kernels.cuh $(CSRC)/hmm_scan.cuh include/pangenie_b200.h
 
-.PHONY: all lib oracle ref clean
-all: lib oracle
+.PHONY: all lib oracle ref tools clean
+all: lib oracle tools
 
 lib: $(LIB)
 $(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS) 2> build_ptxas.log || (cat build_ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS) -lz 2> build_ptxas.log || (cat build_ptxas.log; false)
 	@grep -E "error|warning: v|spill" build_ptxas.log | grep -v "0 bytes spill" | head -40 || true
+
+# C++ host of the `-f` stage over the C-ABI only (no jellyfish, no cereal)
+tools: integration/genotype_from_index
+integration/genotype_from_index: integration/genotype_from_index.cpp include/pangenie_b200.h $(LIB)
+	g++ -std=c++17 -O2 -Wall -Iinclude $< -Lpangenie_b200 -lpangenie_b200 -Wl,-rpath,'$$ORIGIN/../pangenie_b200' -o $@
 
 oracle:
 	$(MAKE) -C oracle oracle
@@ -21,5 +26,5 @@ ref:
 	$(MAKE) -C oracle ref
 
 clean:
-	rm -f $(LIB) build_ptxas.log
+	rm -f $(LIB) build_ptxas.log integration/genotype_from_index
 	$(MAKE) -C oracle clean

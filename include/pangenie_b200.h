@@ -153,6 +153,28 @@ typedef struct {
 } pg_panel;
 
 /* ------------------------------------------------------------------------------------------------
+ * Index artefacts of `PanGenie-index` — what `PanGenie -f <prefix>` loads before the hot path
+ * starts: `<prefix>_UniqueKmersMap.cereal` (cereal binary archive of UniqueKmersMap, src/commands.hpp:11-28, read at
+ * src/commands.cpp:772-778), `<prefix>_<chrom>_kmers.tsv.gz` (src/kmerparser.cpp:16-28, read at src/commands.cpp:98-137)
+ * and the path of `<prefix>_path_segments.fasta` (:764).  Host code, no device needed.  Chromosomes come in the archive's
+ * std::map order, the order the `-f` stage processes them.  The panel arrays are owned by the index (valid until
+ * pg_index_close); `coverage` / `kmer_counts` hold what the archive holds and are overwritten by pg_fill_counts /
+ * pg_genotype_run.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_index pg_index;
+/** with_kmers != 0: also read the k-mer table of every chromosome (needed by the fill step). NULL on error. */
+pg_index* pg_index_open(const char* prefix, int with_kmers);
+/** One archive file only (e.g. a serialised result of the `-f` stage). NULL on error. */
+pg_index* pg_index_open_archive(const char* archive_path);
+void pg_index_close(pg_index* ix);
+uint32_t pg_index_kmer_size(const pg_index* ix);
+uint32_t pg_index_n_chromosomes(const pg_index* ix);
+const char* pg_index_chromosome_name(const pg_index* ix, uint32_t i);
+int pg_index_add_reference(const pg_index* ix);
+const char* pg_index_segments_path(const pg_index* ix);
+int pg_index_panel(pg_index* ix, uint32_t i, pg_panel* out);
+
+/* ------------------------------------------------------------------------------------------------
  * ProbabilityTable (src/probabilitytable.hpp:12-30).  Dense natural-log probabilities for
  * cov in [cov_min, cov_max) x count in [0, count_max); entries outside are computed on the fly with
  * the reference's formulas (src/probabilitytable.cpp:47-65,75-85, src/copynumber.cpp:14-41).

@@ -114,6 +114,8 @@ EXPORTS = [
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
     "pg_count_device_arrays", "pg_count_export_counts", "pg_count_import_counts", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
     "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted", "pg_hmm_run_subsets",
+    "pg_index_open", "pg_index_open_archive", "pg_index_close", "pg_index_kmer_size", "pg_index_n_chromosomes",
+    "pg_index_chromosome_name", "pg_index_add_reference", "pg_index_segments_path", "pg_index_panel",
 ]
 
 
@@ -174,6 +176,15 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "engine_destroy", None, [vp])
         _sig(lib, p + "engine_timings", i32, [vp, C.POINTER(PgTimings)])
         _sig(lib, p + "hmm_run", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgProbTable), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult)])
+        _sig(lib, p + "index_open", vp, [C.c_char_p, i32])
+        _sig(lib, p + "index_open_archive", vp, [C.c_char_p])
+        _sig(lib, p + "index_close", None, [vp])
+        _sig(lib, p + "index_kmer_size", u32, [vp])
+        _sig(lib, p + "index_n_chromosomes", u32, [vp])
+        _sig(lib, p + "index_chromosome_name", C.c_char_p, [vp, u32])
+        _sig(lib, p + "index_add_reference", i32, [vp])
+        _sig(lib, p + "index_segments_path", C.c_char_p, [vp])
+        _sig(lib, p + "index_panel", i32, [vp, u32, C.POINTER(PgPanel)])
         _sig(lib, p + "hmm_run_subsets", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgProbTable), C.POINTER(PgHmmParams), u32, vp, vp,
                                                  C.POINTER(PgHmmResult)])
         _sig(lib, p + "emission_run", i32, [vp, C.POINTER(PgPanel), C.POINTER(PgProbTable), vp, vp, vp])

@@ -9,6 +9,7 @@ Everything computes on the GPU through libpangenie_b200.so; there is no CPU fall
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -341,3 +342,67 @@ class HMM:
 
     def get_genotyping_result(self) -> Result:
         return self.result
+
+
+class Index:
+    """The index artefacts of `PanGenie-index` read by the native reader (csrc/index_io.cu, pg_index_*): what
+    `PanGenie -f <prefix>` loads before the hot path starts (reference src/commands.cpp:760-790, 98-137)."""
+
+    def __init__(self, prefix: str | None = None, with_kmers: bool = True, archive: str | None = None):
+        self._lib = capi.load()
+        if archive is not None:
+            self._h = self._lib.pg_index_open_archive(os.fsencode(archive))
+        else:
+            self._h = self._lib.pg_index_open(os.fsencode(prefix), int(with_kmers))
+        if not self._h:
+            raise PgError(-1, self._lib.pg_last_error().decode())
+
+    @property
+    def kmer_size(self) -> int:
+        return int(self._lib.pg_index_kmer_size(self._h))
+
+    @property
+    def add_reference(self) -> bool:
+        return bool(self._lib.pg_index_add_reference(self._h))
+
+    @property
+    def segments_path(self) -> str:
+        return self._lib.pg_index_segments_path(self._h).decode()
+
+    @property
+    def chromosomes(self):
+        return [self._lib.pg_index_chromosome_name(self._h, i).decode() for i in range(self._lib.pg_index_n_chromosomes(self._h))]
+
+    def panel(self, i: int) -> Panel:
+        """Chromosome i as a Panel (numpy COPIES of the index-owned arrays)."""
+        ps = PgPanel()
+        _check(self._lib, self._lib.pg_index_panel(self._h, i, C.byref(ps)))
+        V, P = ps.n_variants, ps.n_paths
+
+        def arr(addr, n, dt):
+            if not addr or n == 0:
+                return np.zeros(0, dt) if addr or n == 0 else None
+            return np.ctypeslib.as_array(C.cast(addr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+        koff = arr(ps.kmer_offsets, V + 1, np.uint32)
+        aoff = arr(ps.allele_offsets, V + 1, np.uint32)
+        K, A = int(koff[-1]) if V else 0, int(aoff[-1]) if V else 0
+        pan = Panel(P, arr(ps.positions, V, np.uint64), arr(ps.path_to_allele, V * P, np.uint16), arr(ps.coverage, V, np.uint16),
+                    koff, arr(ps.kmer_counts, K, np.uint16), aoff, arr(ps.allele_ids, A, np.uint16),
+                    arr(ps.allele_undefined, A, np.uint8), arr(ps.allele_kmer_offset, A, np.uint16), arr(ps.allele_kmer_mask, A, np.uint32))
+        if ps.flank_offsets:
+            foff = arr(ps.flank_offsets, V + 1, np.uint32)
+            pan.kmer_codes = arr(ps.kmer_codes, K, np.uint64)
+            pan.flank_offsets = foff
+            pan.flank_codes = arr(ps.flank_codes, int(foff[-1]) if V else 0, np.uint64)
+        return pan
+
+    def close(self):
+        if self._h:
+            self._lib.pg_index_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -70,3 +70,32 @@ def test_oracle_hmm_on_fixture_matches_reference(oracle, ref):
     a = oracles.cpu_hmm_run(oracle, "pgo_", [want], table, recombrate=1.26, effective_N=0.00001)[0]
     b = oracles.cpu_hmm_run(ref, "pgr_", [want], table, recombrate=1.26, effective_N=0.00001)[0]
     assert_results_close(a, b, rtol=1e-12, label="fixture")
+
+
+@pytest.mark.gpu
+def test_cpp_host_runs_the_stage_from_the_index_files(engine):
+    """integration/genotype_from_index.cpp: a C++ host over the C-ABI only (native index reader -> pg_genotype_run).
+    Its output equals what the Python mirror computes from the same index prefix and reads."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "integration", "genotype_from_index")
+    if not os.path.exists(exe):
+        pytest.skip("integration/genotype_from_index not built (make tools)")
+    out = subprocess.run([exe, os.path.join(G, "index"), os.path.join(G, "region-reads.fa")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split("\t") for l in out.stdout.splitlines() if not l.startswith("#")]
+    ix = pg.Index(os.path.join(G, "index"))
+    panel = ix.panel(0)
+    reads = np.fromfile(os.path.join(G, "region-reads.fa"), np.uint8)
+    segs = np.fromfile(ix.segments_path, np.uint8)
+    res, peak = engine.genotype_run(reads, segs, [panel], k=ix.kmer_size, recombrate=1.26, effective_N=0.00001)
+    assert f"peak: {peak}" in out.stderr
+    assert len(rows) == panel.n_variants == 2
+    for v, row in enumerate(rows):
+        assert row[0] == "chr1" and int(row[1]) == int(panel.positions[v])
+        gt = tuple(int(x) for x in row[2].split("/")) if row[2] != "./." else (-1, -1)
+        assert gt == tuple(int(x) for x in res[0].genotype[2 * v:2 * v + 2])
+        assert int(row[3]) == int(res[0].quality[v]) and int(row[4]) == int(res[0].unique_kmers[v]) and int(row[5]) == int(res[0].coverage[v])
+        lik = np.array([float(x) for x in row[6].split(",")])
+        want = res[0].likelihoods[int(res[0].gl_offsets[v]):int(res[0].gl_offsets[v + 1])]
+        np.testing.assert_allclose(lik, want, rtol=1e-5, atol=1e-12)
