@@ -16,7 +16,9 @@
 //
 // Decomposition (DESIGN.md "HMM schedule"):
 //   phase 1 "skeleton": one CTA per (chromosome, direction) walks the whole chain, state in registers,
-//            storing a checkpoint every B columns.  Latency bound (one barrier + two reductions per column).
+//            storing a dense P x P checkpoint every B columns.  Latency bound (one barrier + two reductions per
+//            column).  For P <= 9 the checkpoints come from the parallel-in-time kernels of hmm_scan.cuh instead and
+//            this kernel only runs for chromosomes those kernels flagged (a column total underflowed to zero).
 //   phase 2 "blocks":   every block of B columns is independent given its two checkpoints; a CTA recomputes
 //            forward (storing F_t: 8 P^2 bytes per column), then backward fusing the posterior (reading F_t
 //            back).  All SMs busy: this is the HBM-bound kernel the roofline is reported for.

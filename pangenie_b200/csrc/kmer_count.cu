@@ -7,11 +7,16 @@
 //   Bucket-linear probing from a 2-multiply mix of the k-mer, load <= 0.6: a lookup is normally ONE latency round.
 //
 // Text pipeline (per chunk of the read/segment file resident in HBM), all on one stream:
-//   tile_lines_kernel   newline count + last-newline position per 8064-byte tile   (streams the text once)
+//   tile_lines_kernel   newline count + last-newline position per 3968-byte tile advance   (streams the text once)
 //   tile_scan_kernel    exclusive scan over tiles -> line phase / header state at each tile start + carry
-//   count_tile_kernel   per tile: 128-bit loads -> per-byte line classification (block scan) -> compaction of
-//                       sequence symbols into shared memory -> rolling canonical k-mers (16 per thread) ->
-//                       hash probes, 4 independent loads in flight per thread, warp-aggregated atomics.
+//   count_tile_kernel   per 4096-byte tile: 128-bit loads -> per-byte line classification (block scan) -> emitted
+//                       symbols packed 2 bits each into a shared-memory stream -> k-mers by funnel-shift extraction,
+//                       start positions dealt round-robin -> either probed directly (4 k-mers = 8 key loads in
+//                       flight per thread, warp-aggregated atomics) or appended to the buffer of their table partition
+//   probe_parts_kernel  (partitioned mode: table >> L2, resident text) works through the partition buffers in order,
+//                       so the slice of the table being probed stays L2-resident
+// Host text reaches the device through a ring of four 16 MiB staging buffers on a copy stream that runs ahead of the
+// kernels; PRIME and UPDATE of one sample are enqueued back to back.
 // Algorithmic bytes: text bytes + 16 B per k-mer (8 B key probe + RMW of the count sector).
 #include <algorithm>
 #include <cstdio>
@@ -31,7 +36,6 @@ constexpr int CT_HALO = 128;                          // look-ahead so k-mers ma
 constexpr int CT_ADV = CT_TILE - CT_HALO;             // tile advance (multiple of 16)
 constexpr uint64_t CHUNK_BYTES = 64ull << 20;         // chunk of device-resident text processed per launch set (multiple of 16)
 constexpr uint64_t STAGE_BYTES = 16ull << 20;         // host text is streamed through a ring of staging buffers of this size
-constexpr int SYM_PAD = 64;
 
 // scalars[] slots
 enum { SC_DISTINCT = 0, SC_ERROR = 1, SC_CARRY = 2, SC_KMERS = 3, SC_COUNT_SUM = 4, SC_N = 8 };
