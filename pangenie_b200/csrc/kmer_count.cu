@@ -727,6 +727,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 // Works through the partition buffers in partition order (persistent CTAs pulling items of PP_ITEM k-mers), so the
 // CTAs running at any moment hit one or two adjacent slices of the table.
 constexpr int PP_ITEM = 8192;
+constexpr bool PP_QUEUE = false;  // park overflow walks in a shared-memory queue (barriers per item) or walk in place
 constexpr int PP_BATCH = 4;  // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
 template <int OP>
 __global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, const TableRef T) {
@@ -778,9 +779,9 @@ __global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2
         const uint32_t jn = j + PP_BATCH * 256;
         nx[i] = jn < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + jn)) : 0ull;
       }
-      probeN<OP, true, PP_BATCH>(cn, vm, T, inserted, &s_wq);
+      probeN<OP, PP_QUEUE, PP_BATCH>(cn, vm, T, inserted, &s_wq);
     }
-    if (OP == PG_OP_UPDATE) drain_walks(&s_wq, T);
+    if (PP_QUEUE && OP == PG_OP_UPDATE) drain_walks(&s_wq, T);
   }
   for (int o = 16; o > 0; o >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
   if ((tid & 31) == 0 && inserted) atomicAdd(T.scalars + SC_DISTINCT, (unsigned long long)inserted);
