@@ -281,6 +281,8 @@ def main():
                          "least as many chromosomes as GPUs")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("PG_BENCH_INFLIGHT", "2")),
                     help="independent samples kept in flight per GPU in the timed regions (host threads x engines); 1 = one call at a time")
+    ap.add_argument("--inflight-e2e", type=int, default=int(os.environ.get("PG_BENCH_INFLIGHT_E2E", "3")),
+                    help="samples in flight in the end-to-end region (the PCIe transfer of one sample hides the stages of two others)")
     ap.add_argument("--cpu-sample-mb", type=float, default=24.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -348,10 +350,11 @@ def main():
     # results.  `serial` numbers (one sample at a time, the latency of one call) are reported beside them.
     import copy
     D = max(1, args.inflight)
-    engines = [eng] + [pg.Engine(local) for _ in range(D - 1)]
-    panel_sets = [wl.panels] + [copy.deepcopy(wl.panels) for _ in range(D - 1)]
+    De = max(1, args.inflight_e2e)
+    engines = [eng] + [pg.Engine(local) for _ in range(max(D, De) - 1)]
+    panel_sets = [wl.panels] + [copy.deepcopy(wl.panels) for _ in range(max(D, De) - 1)]
 
-    def run_in_flight(step_fn, steps):
+    def run_in_flight(step_fn, steps, D=D):
         """steps calls of step_fn(lane) spread over D host threads; returns wall seconds (device-synchronised)."""
         per = [steps // D + (1 if i < steps % D else 0) for i in range(D)]
         errs = []
@@ -382,10 +385,10 @@ def main():
     # ---- value: inputs resident in HBM ----
     reads_d = reads_h.cuda()
     segs_d = segs_h.cuda()
-    for e_, ps_ in zip(engines, panel_sets):
+    for e_, ps_ in zip(engines[:D], panel_sets[:D]):
         e_.load(ps_)
     for _ in range(W):
-        for e_ in engines:
+        for e_ in engines[:D]:
             e_.run_resident(reads_d, segs_d, k=wl.k, **kw)
     # a step lasts a few ms: keep warming up until the clocks have ramped (at least 0.3 s of work, still untimed)
     t_w = time.perf_counter()
@@ -419,14 +422,14 @@ def main():
     # ---- e2e: pinned host buffers through pg_genotype_run, copies inside the timed region ----
     from pangenie_b200.panel import Result
     res_bufs = [[Result(p) for p in ps_] for ps_ in panel_sets]  # caller-owned output buffers, reused across steps
-    out = [None] * D
+    out = [None] * len(engines)
 
     def e2e_step(i):
         out[i] = engines[i].genotype_run(reads_h, segs_h, panel_sets[i], k=wl.k, results=res_bufs[i], **kw)
     for _ in range(2):
-        for i in range(D):
+        for i in range(De):
             e2e_step(i)
-    dte = run_in_flight(e2e_step, K)
+    dte = run_in_flight(e2e_step, K, De)
     res_e2e, peak = out[0]
     barrier()
     t0s = time.perf_counter()
@@ -486,7 +489,8 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {**config, "l2_flush": "256 MiB memset between steps",
-                       "samples_in_flight": f"{D} per GPU (one host thread + one engine each); serial_ms_per_step = one call at a time"},
+                       "samples_in_flight": f"{D} per GPU in the resident region, {De} in the end-to-end region (one host thread + one engine each); "
+                                            "serial_ms_per_step = one call at a time"},
             "serial_ms_per_step": serial_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dte / K,
