@@ -58,6 +58,13 @@ int pgo_hmm_run(uint32_t n_chrom, const pg_panel* panels, const pg_probtable* ta
 int pgo_hmm_run_mt(uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
                    const pg_hmm_params* params, pg_hmm_result* results, int threads);
 
+/* ---- HaplotypeSampler (src/haplotypesampler.cpp, samplingemissions.cpp, samplingtransitions.cpp): groundwork for
+ * SURVEY.md 8f row 3; no product counterpart yet.  n_out = size + (add_reference ? 1 : 0);
+ * sampled_paths [n_out][V], best_scores [size], new_path_to_allele [V][n_out], new_kmer_count [V], new_counts [<= K]. */
+int pgo_haplotype_sample(const pg_panel* panel, uint32_t size, double recombrate, double effective_N, int add_reference,
+                         uint16_t allele_penalty, uint64_t* sampled_paths, uint32_t* best_scores,
+                         uint16_t* new_path_to_allele, uint32_t* new_kmer_count, uint16_t* new_counts);
+
 #ifdef __cplusplus
 }
 #endif

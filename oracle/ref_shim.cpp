@@ -22,6 +22,7 @@
 #include "biallelicuniquekmers.hpp"
 #include "emissionprobabilitycomputer.hpp"
 #include "histogram.hpp"
+#include "haplotypesampler.hpp"
 #include "hmm.hpp"
 #include "multiallelicuniquekmers.hpp"
 #include "probabilitytable.hpp"
@@ -232,6 +233,40 @@ extern "C" int pgr_histogram_peak(const uint64_t* bins, uint64_t n, int largest_
     std::vector<size_t> ids, vals;
     h.find_peaks(ids, vals);
     *peak = compute_kmer_coverage(ids, vals, largest_peak != 0);
+    return PG_OK;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return PG_ERR_ARG;
+  }
+}
+
+/** HaplotypeSampler(&unique_kmers, size, recombrate, effective_N, &best_scores, add_reference, "", "None", allele_penalty)
+ *  (src/haplotypesampler.cpp:20-78), the reference's own class on objects rebuilt from the flat panel.
+ *  n_out = size + (add_reference ? 1 : 0).  Outputs:
+ *    sampled_paths       [n_out][V]  path id chosen by Viterbi pass i at every variant (get_sampled_paths())
+ *    best_scores         [size]      DP score of every pass
+ *    new_path_to_allele  [V][n_out]  get_allele(j) of the UPDATED UniqueKmers (update_unique_kmers(), :289-303)
+ *    new_kmer_count      [V]         size() of the updated objects, new_counts: their get_readcount_of(i), concatenated */
+extern "C" int pgr_haplotype_sample(const pg_panel* panel, uint32_t size, double recombrate, double effective_N,
+                                    int add_reference, uint16_t allele_penalty, uint64_t* sampled_paths,
+                                    uint32_t* best_scores, uint16_t* new_path_to_allele, uint32_t* new_kmer_count,
+                                    uint16_t* new_counts) {
+  try {
+    UKVec uk;
+    build_unique_kmers(panel, uk);
+    std::vector<unsigned int> scores;
+    HaplotypeSampler sampler(&uk, size, recombrate, (long double)effective_N, &scores, add_reference != 0, "", "None", allele_penalty);
+    SampledPaths sp = sampler.get_sampled_paths();
+    const size_t V = panel->n_variants, n_out = sp.sampled_paths.size();
+    for (size_t i = 0; i < n_out; ++i)
+      for (size_t v = 0; v < V; ++v) sampled_paths[i * V + v] = sp.sampled_paths[i][v];
+    for (size_t i = 0; i < scores.size(); ++i) best_scores[i] = scores[i];
+    size_t k = 0;
+    for (size_t v = 0; v < V; ++v) {
+      for (size_t j = 0; j < n_out; ++j) new_path_to_allele[v * n_out + j] = uk[v]->get_allele(j);
+      new_kmer_count[v] = (uint32_t)uk[v]->size();
+      for (size_t i = 0; i < uk[v]->size(); ++i) new_counts[k++] = uk[v]->get_readcount_of(i);
+    }
     return PG_OK;
   } catch (std::exception& e) {
     g_err = e.what();

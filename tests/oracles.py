@@ -150,3 +150,24 @@ class OracleCounter:
             self.lib.pgo_count_destroy(self.h)
         except Exception:
             pass
+
+
+def cpu_haplotype_sample(lib, prefix, panel, size, recombrate=1.26, effective_N=25000.0, add_reference=False, allele_penalty=10):
+    """pgo_/pgr_ haplotype_sample -> (sampled_paths [n_out, V], best_scores [size], new_path_to_allele [V, n_out],
+    new_kmer_count [V], new_counts) — the reference's HaplotypeSampler / its CPU restatement (oracle/pg_oracle_sampler.cpp)."""
+    V, n_out = panel.n_variants, size + (1 if add_reference else 0)
+    paths = np.zeros((n_out, V), np.uint64)
+    scores = np.zeros(size, np.uint32)
+    p2a = np.zeros((V, n_out), np.uint16)
+    nk = np.zeros(V, np.uint32)
+    counts = np.zeros(max(len(panel.kmer_counts), 1), np.uint16)
+    ps = panel.as_struct()
+    f = getattr(lib, prefix + "haplotype_sample")
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(PgPanel), C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_uint16, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p]
+    st = f(C.byref(ps), size, recombrate, effective_N, int(add_reference), allele_penalty, ptr(paths), ptr(scores), ptr(p2a),
+           ptr(nk), ptr(counts))
+    if st != 0:
+        raise RuntimeError(getattr(lib, prefix + "last_error")().decode())
+    return paths, scores, p2a, nk, counts[:int(nk.sum())]

@@ -75,3 +75,22 @@ def test_reference_catch_suite_passes_over_the_restatement():
     tail = [l for l in out.splitlines() if l.startswith("assertions:")][-1]
     assert "552 passed | 1 failed" in tail or "All tests passed" in out, tail
     assert "HMMTest.cpp:438" in out  # the phasing (Viterbi) assertion, out of scope
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_haplotype_sampler_restatement_matches_reference(oracle, ref, seed):
+    """oracle/pg_oracle_sampler.cpp against the reference's own HaplotypeSampler (src/haplotypesampler.cpp) compiled
+    unmodified: identical Viterbi paths, scores, sampled panels and surviving k-mer counts (integer work: exact)."""
+    rng = np.random.default_rng(300 + seed)
+    n_paths = int(rng.choice([2, 3, 8, 20, 64]))
+    panel = random_panel(rng, int(rng.integers(2, 120)), n_paths, max_alleles=int(rng.choice([2, 2, 4])),
+                         undefined_frac=0.1 if seed % 2 else 0.0, shared_kmer_frac=0.3, ref_only_frac=0.1,
+                         kmers_per_allele=(0, 8), count_range=(0, 12), spacing=(50, 200000))
+    for size, add_ref, penalty, eff_n in ((1, False, 10, 25000.0), (min(n_paths, 5), True, 5, 0.01), (n_paths, False, 10, 1e-5)):
+        a = oracles.cpu_haplotype_sample(oracle, "pgo_", panel, size, effective_N=eff_n, add_reference=add_ref, allele_penalty=penalty)
+        b = oracles.cpu_haplotype_sample(ref, "pgr_", panel, size, effective_N=eff_n, add_reference=add_ref, allele_penalty=penalty)
+        for x, y, what in zip(a, b, ("paths", "scores", "path_to_allele", "kmer counts per variant", "counts")):
+            assert np.array_equal(x, y), (what, size, add_ref)
+        # every (variant, path) is used by at most one pass
+        for v in range(panel.n_variants):
+            assert len(set(a[0][:size, v].tolist())) == size
