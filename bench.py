@@ -181,8 +181,16 @@ def cpu_pipeline(wl, threads: int, sample_bytes: int, filled_panels_ok: bool):
         kind = "port"
     t_hmm = time.perf_counter() - t0
     t_total = t_prime + t_update + t_fill + t_hmm
+    cpu_model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                cpu_model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
     return {
-        "value": wl.n_variants / t_total, "unit": "variants/s", "cores": threads, "kind": kind,
+        "value": wl.n_variants / t_total, "unit": "variants/s", "cores": threads, "cpu_model": cpu_model, "kind": kind,
         "sample": (f"emission+HMM: reference hmm.cpp on the full panel, {hthreads} thread(s) (one per chromosome, commands.cpp:949-978), "
                    f"{t_hmm:.3f}s; counting: CPU restatement of the jellyfish path (not libjellyfish), {threads} threads, PRIME full segments "
                    f"{t_prime:.2f}s + UPDATE on the first {sample / 1e6:.1f} MB of {total / 1e6:.1f} MB reads {t_update_sample:.2f}s "
