@@ -15,7 +15,8 @@
  * Conventions: plain C structs, caller-owned HOST buffers unless a name ends in `_device`, int status
  * (0 = PG_OK) + pg_last_error() (thread-local string), no exceptions / STL / torch types across the
  * boundary, explicit device ordinal per handle, no global state.  Read-only calls on a finished
- * counter are safe from several host threads.  There is NO CPU fallback: every compute entry point
+ * counter (lookups, histogram, coverage) are safe from several host threads: lookups run on private streams and buffers,
+ * the histogram / coverage calls serialise on a per-counter lock around their shared scratch.  There is NO CPU fallback: every compute entry point
  * fails with PG_ERR_CUDA when no sm_100-class device can be opened.
  */
 #ifndef PANGENIE_B200_H
@@ -41,6 +42,9 @@ const char* pg_last_error(void);
 const char* pg_version(void);
 /** Number of usable CUDA devices (0 if none; never throws). */
 int pg_device_count(void);
+/** Kernels this library has launched from the calling host thread so far (measurement hook: bench.py reports the
+ *  difference over its timed region as `gpu_launches`). */
+uint64_t pg_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Seam 1: KmerCounter  (src/kmercounter.hpp:9-24)
@@ -63,7 +67,8 @@ typedef struct pg_counter pg_counter;
  * `hash_size` is the `-e` value: in PRIME/UPDATE mode the table is sized from the segment file and
  * `hash_size` is only a lower bound; in count-all mode it is the number of distinct k-mers the table
  * must hold (jellyfish grows its table, this one fails with PG_ERR_FULL).  `nr_threads` of the
- * reference has no meaning here.  Files are streamed through pinned buffers (uncompressed FASTA/FASTQ).
+ * reference has no meaning here.  Both files are streamed: file -> ring of pinned staging buffers -> device, never held in
+ * host memory as a whole (uncompressed FASTA / 4-line FASTQ; anything else fails with PG_ERR_FORMAT).
  * Returns NULL on error.
  */
 pg_counter* pg_count_create(const char* reads_path, const char* segments_path, uint32_t k,
@@ -111,9 +116,22 @@ int pg_count_compute_histogram(const pg_counter* c, uint64_t max_count, int larg
 int pg_count_device_arrays(const pg_counter* c, uint64_t* slots_addr, uint64_t* counts_addr, uint64_t* capacity);
 int pg_count_export_counts(pg_counter* c);
 int pg_count_import_counts(pg_counter* c);
-/** k-mers processed / device milliseconds of the last pg_count_feed* call (measurement hooks). */
+/** Rewrites the keys of a PRIMEd table (all counts still zero) into the canonical layout: every run of consecutive full
+ *  buckets sorted by (home bucket, k-mer).  The layout then depends on the SET of primed k-mers only, not on the order the
+ *  insertions happened to win, so every GPU that PRIMEs the same segment file into a table of the same capacity holds the
+ *  identical array and the per-GPU count arrays can be added position by position: the sample needs ONE all-reduce and no
+ *  broadcast of the table.  Lookups are unaffected. */
+int pg_count_canonicalize(pg_counter* c);
+/** The same exchange in pieces, so the contiguous staging array need not be as large as the table: the buffer holds
+ *  `n_slots` u32 counts (multiple of 4); export/import move the counts of slots [first_slot, first_slot + n_slots). */
+int pg_count_exchange_buffer(pg_counter* c, uint64_t n_slots, uint64_t* addr);
+int pg_count_export_range(pg_counter* c, uint64_t first_slot, uint64_t n_slots);
+int pg_count_import_range(pg_counter* c, uint64_t first_slot, uint64_t n_slots);
+/** k-mers processed / device milliseconds of the last pg_count_feed* call (measurement hooks); pg_count_last_probe_ms:
+ *  the part of it spent in the probe passes over the partition buffers (0 when the pass probed directly), and their number. */
 uint64_t pg_count_kmers_seen(const pg_counter* c);
 double pg_count_last_ms(const pg_counter* c);
+double pg_count_last_probe_ms(const pg_counter* c, uint32_t* n_passes);
 
 /** Number of distinct keys / slots (diagnostics). */
 uint64_t pg_count_distinct(const pg_counter* c);
@@ -316,6 +334,8 @@ typedef struct {
   uint64_t text_bytes;         /* read text bytes streamed                                          */
   double prime_ms;             /* PRIME pass over the segment file                                  */
   uint64_t hmm_scan_used;      /* 1 if the checkpoints came from the parallel-in-time scan path (P <= 9) */
+  double count_probe_ms;       /* part of count_ms spent in probe_parts_kernel (partitioned counting)  */
+  uint64_t count_probe_passes; /* launches of probe_parts_kernel in the UPDATE/COUNT pass              */
 } pg_timings;
 int pg_engine_timings(const pg_engine* e, pg_timings* out);
 

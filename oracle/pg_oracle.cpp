@@ -62,10 +62,17 @@ struct pgo_counter {
     mask = cap - 1;
     keys.reset(new std::atomic<uint64_t>[cap]);
     vals.reset(new std::atomic<uint64_t>[cap]);
-    for (uint64_t i = 0; i < cap; ++i) {
-      keys[i].store(EMPTY, std::memory_order_relaxed);
-      vals[i].store(0, std::memory_order_relaxed);
-    }
+    // first touch in parallel: the initialisation of a table for a whole genome is otherwise the slowest part of PRIME
+    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)(cap >> 20) + 1u));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t)
+      pool.emplace_back([this, t, nt]() {
+        for (uint64_t i = cap * t / nt; i < cap * (t + 1) / nt; ++i) {
+          keys[i].store(EMPTY, std::memory_order_relaxed);
+          vals[i].store(0, std::memory_order_relaxed);
+        }
+      });
+    for (auto& th : pool) th.join();
   }
   void reserve(uint64_t want_distinct) {
     const uint64_t need = (uint64_t)(want_distinct / 0.5) + 1024;

@@ -18,6 +18,8 @@
 #include <thread>
 #include <vector>
 
+#include <chrono>
+
 #include "../include/pangenie_b200.h"
 #include "biallelicuniquekmers.hpp"
 #include "emissionprobabilitycomputer.hpp"
@@ -89,14 +91,16 @@ ProbabilityTable build_table(const pg_probtable* t) {
   return probs;
 }
 
-int run_one(const pg_panel* panel, ProbabilityTable* probs, const pg_hmm_params* prm, pg_hmm_result* res) {
+int run_one(const pg_panel* panel, ProbabilityTable* probs, const pg_hmm_params* prm, pg_hmm_result* res, double* hmm_seconds = nullptr) {
   UKVec uk;
-  build_unique_kmers(panel, uk);
+  build_unique_kmers(panel, uk);   // (the reference deserialises these objects; not part of run_genotyping)
   std::vector<unsigned short> only;
   if (prm->only_paths) only.assign(prm->only_paths, prm->only_paths + prm->n_only_paths);
+  const auto t0 = std::chrono::steady_clock::now();
   HMM hmm(&uk, probs, true, false, prm->recombrate, prm->uniform != 0, (long double)prm->effective_N,
           prm->only_paths ? &only : nullptr, prm->normalize != 0);
   std::vector<GenotypingResult> gr = hmm.move_genotyping_result();
+  if (hmm_seconds) *hmm_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   ColumnIndexer indexer(&uk, prm->only_paths ? &only : nullptr);
   std::memset(res->is_column, 0, panel->n_variants);
   for (size_t c = 0; c < indexer.size(); ++c) res->is_column[indexer.get_variant_id(c)] = 1;
@@ -127,12 +131,15 @@ int run_one(const pg_panel* panel, ProbabilityTable* probs, const pg_hmm_params*
 
 extern "C" const char* pgr_last_error(void) { return g_err.c_str(); }
 
-extern "C" int pgr_hmm_run_mt(uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
-                              const pg_hmm_params* params, pg_hmm_result* results, int threads) {
+/** As pgr_hmm_run_mt; additionally chrom_seconds[c] (may be NULL) receives the wall seconds chromosome c spent inside the
+ *  reference's `HMM` constructor + move_genotyping_result (what run_genotyping executes per job, commands.cpp:155-171),
+ *  excluding the re-creation of the UniqueKmers objects from the flat panel. */
+extern "C" int pgr_hmm_run_timed(uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
+                                 const pg_hmm_params* params, pg_hmm_result* results, int threads, double* chrom_seconds) {
   try {
     ProbabilityTable probs = build_table(table);
     if (threads <= 1 || n_chrom == 1) {
-      for (uint32_t c = 0; c < n_chrom; ++c) run_one(&panels[c], &probs, params, &results[c]);
+      for (uint32_t c = 0; c < n_chrom; ++c) run_one(&panels[c], &probs, params, &results[c], chrom_seconds ? chrom_seconds + c : nullptr);
       return PG_OK;
     }
     // one job per chromosome on a fixed pool (commands.cpp:949-978)
@@ -150,7 +157,7 @@ extern "C" int pgr_hmm_run_mt(uint32_t n_chrom, const pg_panel* panels, const pg
             c = next++;
           }
           try {
-            run_one(&panels[c], &probs, params, &results[c]);
+            run_one(&panels[c], &probs, params, &results[c], chrom_seconds ? chrom_seconds + c : nullptr);
           } catch (std::exception& e) {
             std::lock_guard<std::mutex> lk(mu);
             err = e.what();
@@ -167,6 +174,11 @@ extern "C" int pgr_hmm_run_mt(uint32_t n_chrom, const pg_panel* panels, const pg
     g_err = e.what();
     return PG_ERR_ARG;
   }
+}
+
+extern "C" int pgr_hmm_run_mt(uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,
+                              const pg_hmm_params* params, pg_hmm_result* results, int threads) {
+  return pgr_hmm_run_timed(n_chrom, panels, table, params, results, threads, nullptr);
 }
 
 extern "C" int pgr_hmm_run(uint32_t n_chrom, const pg_panel* panels, const pg_probtable* table,

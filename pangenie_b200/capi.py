@@ -100,12 +100,14 @@ class PgTimings(C.Structure):
         ("text_bytes", C.c_uint64),
         ("prime_ms", C.c_double),
         ("hmm_scan_used", C.c_uint64),
+        ("count_probe_ms", C.c_double),
+        ("count_probe_passes", C.c_uint64),
     ]
 
 
 # every symbol include/pangenie_b200.h declares (tests check the .so exports each one)
 EXPORTS = [
-    "pg_last_error", "pg_version", "pg_device_count",
+    "pg_last_error", "pg_version", "pg_device_count", "pg_kernel_launches", "pg_count_last_probe_ms",
     "pg_count_create", "pg_count_create_from_buffers", "pg_count_new", "pg_count_feed", "pg_count_feed_device",
     "pg_count_lookup_ascii", "pg_count_lookup", "pg_count_kmer_coverage", "pg_count_histogram",
     "pg_count_compute_histogram", "pg_count_distinct", "pg_count_capacity", "pg_count_destroy", "pg_histogram_peak",
@@ -113,6 +115,7 @@ EXPORTS = [
     "pg_result_layout", "pg_engine_create", "pg_engine_destroy", "pg_hmm_run", "pg_emission_run",
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
     "pg_count_device_arrays", "pg_count_export_counts", "pg_count_import_counts", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
+    "pg_count_canonicalize", "pg_count_exchange_buffer", "pg_count_export_range", "pg_count_import_range",
     "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted", "pg_hmm_run_subsets",
     "pg_index_open", "pg_index_open_archive", "pg_index_close", "pg_index_kmer_size", "pg_index_n_chromosomes",
     "pg_index_chromosome_name", "pg_index_add_reference", "pg_index_segments_path", "pg_index_panel",
@@ -138,6 +141,7 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
     if has("version"):
         _sig(lib, p + "version", C.c_char_p, [])
         _sig(lib, p + "device_count", i32, [])
+        _sig(lib, p + "kernel_launches", u64, [])
     if has("count_new"):
         if p == "pg_":
             _sig(lib, p + "count_new", vp, [u32, u64, i32])
@@ -150,7 +154,12 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
             _sig(lib, p + "count_import_counts", i32, [vp])
             _sig(lib, p + "count_kmers_seen", u64, [vp])
             _sig(lib, p + "count_last_ms", dbl, [vp])
+            _sig(lib, p + "count_last_probe_ms", dbl, [vp, C.POINTER(u32)])
             _sig(lib, p + "count_clear", i32, [vp])
+            _sig(lib, p + "count_canonicalize", i32, [vp])
+            _sig(lib, p + "count_exchange_buffer", i32, [vp, u64, C.POINTER(u64)])
+            _sig(lib, p + "count_export_range", i32, [vp, u64, u64])
+            _sig(lib, p + "count_import_range", i32, [vp, u64, u64])
         else:
             _sig(lib, p + "count_new", vp, [u32])
             _sig(lib, p + "count_create_from_buffers", vp, [vp, u64, vp, u64, u32])

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -155,7 +156,9 @@ struct pg_counter {
   uint64_t max_distinct = 0;  // keys the caller asked room for
   // [capacity / 4] 64-byte buckets (KmerBucket): a lookup normally costs ONE DRAM burst and one latency round
   pg::KmerBucket* slots = nullptr;
-  uint32_t* d_counts_tmp = nullptr;  // contiguous copy of the counts for the cross-GPU all-reduce
+  uint32_t* d_counts_tmp = nullptr;  // contiguous copy of (a range of) the counts for the cross-GPU all-reduce
+  uint64_t counts_tmp_cap = 0;       // in slots
+  std::mutex scratch_mutex;          // histogram bins / count-sum scratch are shared by concurrent read-only callers
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   // streaming scratch
@@ -181,4 +184,9 @@ struct pg_counter {
   uint32_t* d_part_cursor = nullptr;  // [256]: cursors [0..255), work counter at [255]
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;  // timing events of a PRIME pass enqueued together with its UPDATE pass
   double last_prime_ms = 0.0;
+  // probe passes of the last partitioned feed: event pairs around every probe_parts_kernel launch
+  static constexpr int MAX_PROBE_EV = 256;
+  std::vector<cudaEvent_t> ev_probe;  // 2 per pass, created on demand, reused
+  int n_probe = 0;
+  double last_probe_ms = 0.0;
 };

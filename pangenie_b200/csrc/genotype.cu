@@ -1319,6 +1319,8 @@ extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32
     PG_TRY(pg_count_feed(c, in->reads, in->reads_len, PG_OP_COUNT));
   }
   e->tm.count_ms = c->last_feed_ms;
+  e->tm.count_probe_ms = c->last_probe_ms;
+  e->tm.count_probe_passes = (uint64_t)c->n_probe;
   e->tm.kmers_counted = c->kmers_seen;
   e->tm.text_bytes = in->reads_len;
   tr.mark("count");
@@ -1407,6 +1409,8 @@ extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_
   }
   tr.mark("count");
   e->tm.count_ms = c->last_feed_ms;
+  e->tm.count_probe_ms = c->last_probe_ms;
+  e->tm.count_probe_passes = (uint64_t)c->n_probe;
   e->tm.kmers_counted = c->kmers_seen;
   e->tm.text_bytes = reads_len;
   PG_TRY(engine_after_count(e, c, d_segments != nullptr, regularization, params, kmer_abundance_peak));

@@ -85,7 +85,8 @@ static double to_log(ld p) { return p > 0 ? (double)logl(p) : -std::numeric_limi
 using namespace pg;
 
 extern "C" const char* pg_last_error(void) { return g_error.c_str(); }
-extern "C" const char* pg_version(void) { return "pangenie_b200 0.1 (sm_100a)"; }
+extern "C" const char* pg_version(void) { return "pangenie_b200 0.2 (sm_100a)"; }
+extern "C" uint64_t pg_kernel_launches(void) { return g_launches; }
 extern "C" int pg_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -18,11 +18,16 @@
 // Host text reaches the device through a ring of four 16 MiB staging buffers on a copy stream that runs ahead of the
 // kernels; PRIME and UPDATE of one sample are enqueued back to back.
 // Algorithmic bytes: text bytes + 16 B per k-mer (8 B key probe + RMW of the count sector).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -40,7 +45,7 @@ constexpr uint64_t STAGE_BYTES = 16ull << 20;         // host text is streamed t
 // scalars[] slots
 enum { SC_DISTINCT = 0, SC_ERROR = 1, SC_CARRY = 2, SC_KMERS = 3, SC_COUNT_SUM = 4, SC_N = 8 };
 // error bits
-enum { ERR_PROBE = 1, ERR_HALO = 2 };
+enum { ERR_PROBE = 1, ERR_HALO = 2, ERR_FASTQ = 4 };
 // FASTA line state
 enum { LS_LINE_START = 0, LS_HEADER = 1, LS_SEQ = 2 };
 
@@ -575,13 +580,15 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   // ---- which of my bytes are emitted as symbols (bit mask E, bit i = byte i) ----
   // FASTQ: byte i is emitted iff it lies in a sequence line (line index mod 4 == 1); the newline that ends the
   // sequence line is emitted too: it is not a base, so no k-mer spans records.
-  // FASTA: sequence-line bytes except newlines are emitted (lines of one record are joined); the newline ending a
-  // HEADER line is emitted as the record separator.
+  // FASTA: sequence-line bytes except newlines are emitted (lines of one record are joined); the '>' that opens a
+  // HEADER line is emitted as the record separator (a non-base), the rest of the header is skipped - so a window is
+  // closed as soon as the next record starts, however long its header is.
   uint32_t E = 0;
   if (is_fastq) {
     uint32_t tot;
     uint32_t line = (meta & 3u) + block_exscan_add(__popc(nlbits), s_warp, &tot);
     uint32_t rest = nlbits, start = 0;
+    bool bad_layout = false;
 #pragma unroll 1
     while (true) {
       const uint32_t p = rest ? (uint32_t)__ffs(rest) - 1u : 15u;  // segment [start, p] lies in line `line`
@@ -590,8 +597,16 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
       rest &= rest - 1u;
       ++line;
       start = p + 1u;
+      // 4-line layout check (jellyfish parses '@' header / sequence / '+' / quality; a wrapped sequence or a stray blank
+      // line would silently shift the phase and count quality characters): the line after an owned newline must start
+      // with '@' when it is a header line and with '+' when it is a separator line
+      if (((ownedmask >> p) & 1u) && pos0 + start < n_avail && !(line & 1u)) {
+        const uint32_t c0 = start <= 15u ? byte_of(w, start) : (uint32_t)(uint8_t)text[pos0 + start];
+        bad_layout |= c0 != ((line & 2u) ? (uint32_t)'+' : (uint32_t)'@');
+      }
       if (start > 15u) break;
     }
+    if (bad_layout) atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_FASTQ);
   } else {
     const int my_last = nlbits ? tid * 16 + (31 - __clz(nlbits)) : -1;
     const int last_before = block_exscan_max(my_last, s_warp_i);  // tile-relative index or -1
@@ -605,12 +620,14 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     uint32_t rest = nlbits, start = 0;
 #pragma unroll 1
     while (start < nbytes) {
-      if (state == LS_LINE_START) state = byte_of(w, start) == '>' ? LS_HEADER : LS_SEQ;
+      if (state == LS_LINE_START) {
+        state = byte_of(w, start) == '>' ? LS_HEADER : LS_SEQ;
+        if (state == LS_HEADER) E |= 1u << start;                    // the '>' is the separator symbol
+      }
       const uint32_t p = rest ? (uint32_t)__ffs(rest) - 1u : 16u;  // newline ending this line piece (16: none)
       const uint32_t last = p < 16u ? p : 15u;
       const uint32_t seg = (0xffffu >> (15u - last)) & ~((1u << start) - 1u);
       if (state == LS_SEQ) E |= seg & ~(p < 16u ? (1u << p) : 0u);  // sequence bytes, newline dropped
-      else if (p < 16u) E |= 1u << p;                                // header: only its newline (a non-base)
       if (p >= 16u) break;
       rest &= rest - 1u;
       state = LS_LINE_START;
@@ -645,7 +662,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 
   // halo sufficiency: an open window at the end of the look-ahead means a k-mer may have been cut
   // (only possible with pathological whitespace); report instead of silently miscounting.
-  if (tid == 0 && owned_end == base + CT_ADV && n_avail > base + CT_TILE && n_syms > 0) {
+  if (tid == 0 && n_avail >= owned_end + CT_HALO && n_syms > 0) {
     const uint32_t after = n_syms - n_owned_syms;
     if (after < k - 1 && n_owned_syms > 0) {
       bool open = true;
@@ -844,16 +861,70 @@ __global__ void fill_slots_kernel(KmerBucket* tab, uint64_t cap) {
     q[i] = (i & 3) < 2 ? make_ulonglong2(EMPTY_KEY, EMPTY_KEY) : make_ulonglong2(0ull, 0ull);
 }
 
-// counts <-> contiguous u32 array (the cross-GPU all-reduce runs on the contiguous copy)
-__global__ void export_counts_kernel(const KmerBucket* __restrict__ tab, uint64_t cap, uint32_t* __restrict__ out) {
-  const uint64_t nb = cap >> 2;
+// counts of buckets [b0, b0 + nb) <-> contiguous u32 array (the cross-GPU all-reduce runs on the contiguous copy)
+__global__ void export_counts_kernel(const KmerBucket* __restrict__ tab, uint64_t b0, uint64_t nb, uint32_t* __restrict__ out) {
   for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x)
-    reinterpret_cast<uint4*>(out)[b] = *reinterpret_cast<const uint4*>(tab[b].cnt);
+    reinterpret_cast<uint4*>(out)[b] = *reinterpret_cast<const uint4*>(tab[b0 + b].cnt);
 }
-__global__ void import_counts_kernel(KmerBucket* __restrict__ tab, uint64_t cap, const uint32_t* __restrict__ in) {
-  const uint64_t nb = cap >> 2;
+__global__ void import_counts_kernel(KmerBucket* __restrict__ tab, uint64_t b0, uint64_t nb, const uint32_t* __restrict__ in) {
   for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x)
-    *reinterpret_cast<uint4*>(tab[b].cnt) = reinterpret_cast<const uint4*>(in)[b];
+    *reinterpret_cast<uint4*>(tab[b0 + b].cnt) = reinterpret_cast<const uint4*>(in)[b];
+}
+
+// Canonical key layout after PRIME.  Which key sits where depends on the order the CAS insertions happened to win, so
+// two GPUs that PRIME the same segment file hold the same SET of occupied positions (a property of linear probing) but
+// not the same array.  A "run" is a maximal sequence of consecutive full buckets plus the bucket that ends it; its keys
+// occupy consecutive positions starting at the first bucket, and none of them has its home bucket before the run.
+// Sorting every run by (home bucket, key) gives a layout that depends on the key set only: every key still lies at or
+// after its home with full buckets in between (the i-th key of a sorted run has at least 4*home keys before it), so
+// lookups are unaffected, and the count arrays of all GPUs can be added position by position (ONE all-reduce, no broadcast
+// of the table).  One thread per run start; runs are a single bucket in ~85% of the cases at load <= 0.6.
+__device__ __forceinline__ bool key_before(uint64_t ha, uint64_t ka, uint64_t hb, uint64_t kb) { return ha < hb || (ha == hb && ka < kb); }
+__global__ void __launch_bounds__(256) canonicalize_kernel(KmerBucket* __restrict__ tab, uint64_t nb, uint32_t q, uint32_t sh,
+                                                            unsigned long long* __restrict__ scalars) {
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t prev = b == 0 ? nb - 1 : b - 1;
+    if (tab[prev].key[3] != EMPTY_KEY) continue;  // the previous bucket is full: b continues its run
+    // length of the run in positions: consecutive full buckets, then the occupied prefix of the first non-full one
+    uint64_t n = 0, e = b;
+    while (true) {
+      const ulonglong2 kb2 = *reinterpret_cast<const ulonglong2*>(&tab[e].key[2]);
+      if (kb2.y != EMPTY_KEY) {
+        n += 4;
+        e = e + 1 == nb ? 0 : e + 1;
+        if (n >= 4 * nb) break;  // table completely full: cannot happen below the design load
+        continue;
+      }
+      const ulonglong2 ka2 = *reinterpret_cast<const ulonglong2*>(&tab[e].key[0]);
+      n += ka2.x == EMPTY_KEY ? 0 : ka2.y == EMPTY_KEY ? 1 : kb2.x == EMPTY_KEY ? 2 : 3;
+      break;
+    }
+    if (n < 2) continue;
+    // position i of the run = position (i & 3) of bucket (b + i / 4) mod nb; home distance from b is measured modulo nb
+    auto slot_ptr = [&](uint64_t i) -> unsigned long long* {
+      uint64_t bb = b + (i >> 2);
+      if (bb >= nb) bb -= nb;
+      return &tab[bb].key[i & 3];
+    };
+    auto home_rel = [&](uint64_t key) -> uint64_t {
+      const uint64_t h = home_slot(key, q, sh) >> 2;
+      return h >= b ? h - b : h + nb - b;
+    };
+    // insertion sort in place (runs are short; the keys of one run are touched by this thread only)
+    for (uint64_t i = 1; i < n; ++i) {
+      const uint64_t key = *slot_ptr(i);
+      const uint64_t hk = home_rel(key);
+      uint64_t j = i;
+      while (j > 0) {
+        const uint64_t other = *slot_ptr(j - 1);
+        if (!key_before(hk, key, home_rel(other), other)) break;
+        *slot_ptr(j) = other;
+        --j;
+      }
+      if (j != i) *slot_ptr(j) = key;
+      if (4 * hk > j) atomicOr(scalars + SC_ERROR, (unsigned long long)ERR_PROBE);  // would sit before its home: impossible
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -963,34 +1034,51 @@ static int part_flush(pg_counter* c, const PartArgs& pa, int op) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool timed = c->n_probe < pg_counter::MAX_PROBE_EV;
+  if (timed) {
+    while ((int)c->ev_probe.size() < 2 * (c->n_probe + 1)) {
+      cudaEvent_t ev;
+      PG_CUDA(cudaEventCreate(&ev));
+      c->ev_probe.push_back(ev);
+    }
+    PG_CUDA(cudaEventRecord(c->ev_probe[2 * c->n_probe], c->stream));
+  }
   if (op == PG_OP_COUNT) probe_parts_kernel<PG_OP_COUNT><<<sms * 6, 256, 0, c->stream>>>(pa, T);
   else probe_parts_kernel<PG_OP_UPDATE><<<sms * 6, 256, 0, c->stream>>>(pa, T);
   count_launch();
   PG_CUDA(cudaGetLastError());
+  if (timed) {
+    PG_CUDA(cudaEventRecord(c->ev_probe[2 * c->n_probe + 1], c->stream));
+    ++c->n_probe;
+  }
   PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, 256 * sizeof(uint32_t), c->stream));
   return PG_OK;
 }
 
 // Enqueues one pass over `src` (host or device text) without waiting for it: staged copies run on copy_stream ahead of
 // the kernels on c->stream.  ev0/ev1 bracket the pass on c->stream.  feed_finish() waits and checks the error flags.
+// `fd` >= 0: the text is the first `len` bytes of that file, read chunk by chunk into the pinned staging ring (pread), so a
+// read set of any size streams file -> pinned ring -> device without ever being held in host memory as a whole.
 static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cudaEvent_t ev0, cudaEvent_t ev1,
-                        const std::function<int()>* after_first_chunk = nullptr) {
+                        const std::function<int()>* after_first_chunk = nullptr, int fd = -1) {
   if (!c) return fail(PG_ERR_ARG, "null counter");
   if (op < 0 || op > 2) return fail(PG_ERR_ARG, "invalid op");
-  if (!src && len) return fail(PG_ERR_ARG, "null text");
+  if (!src && len && fd < 0) return fail(PG_ERR_ARG, "null text");
   cudaPointerAttributes attr;
   memset(&attr, 0, sizeof(attr));
-  cudaError_t pe = len ? cudaPointerGetAttributes(&attr, src) : cudaSuccess;
+  cudaError_t pe = (len && fd < 0) ? cudaPointerGetAttributes(&attr, src) : cudaSuccess;
   if (pe != cudaSuccess) {
     cudaGetLastError();
     attr.type = cudaMemoryTypeUnregistered;
   }
-  const bool on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
-  const bool pinned = attr.type == cudaMemoryTypeHost;
+  const bool on_device = fd < 0 && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  const bool pinned = fd < 0 && attr.type == cudaMemoryTypeHost;
   int is_fastq = 0;
   if (len) {
     char first = 0;
-    if (on_device) PG_CUDA(cudaMemcpy(&first, src, 1, cudaMemcpyDeviceToHost));
+    if (fd >= 0) {
+      if (pread(fd, &first, 1, 0) != 1) return fail(PG_ERR_IO, "cannot read the sequence file");
+    } else if (on_device) PG_CUDA(cudaMemcpy(&first, src, 1, cudaMemcpyDeviceToHost));
     else first = src[0];
     if (first == '@') is_fastq = 1;
     else if (first == '>') is_fastq = 0;
@@ -999,6 +1087,7 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   // reset per-feed scalars: carry := 0 (FASTQ: header line phase; FASTA: LS_LINE_START), k-mers of this pass := 0
   PG_CUDA(cudaMemsetAsync(c->d_scalars + SC_CARRY, 0, 2 * sizeof(unsigned long long), c->stream));
   static_assert(SC_KMERS == SC_CARRY + 1, "one memset clears both");
+  if (op != PG_OP_PRIME) c->n_probe = 0;
   PG_CUDA(cudaEventRecord(ev0, c->stream));
   const bool direct = on_device && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   if (!direct && len) PG_TRY(ensure_stage(c, !on_device && !pinned));
@@ -1027,7 +1116,16 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
       } else if (pinned) {
         PG_CUDA(cudaMemcpyAsync(c->d_stage[buf], src + off, n + nh, cudaMemcpyHostToDevice, c->copy_stream));
       } else {
-        memcpy(c->h_stage[buf], src + off, n + nh);
+        if (fd >= 0) {
+          uint64_t got = 0;
+          while (got < n + nh) {
+            const ssize_t r = pread(fd, c->h_stage[buf] + got, n + nh - got, (off_t)(off + got));
+            if (r <= 0) return fail(PG_ERR_IO, "short read on the sequence file");
+            got += (uint64_t)r;
+          }
+        } else {
+          memcpy(c->h_stage[buf], src + off, n + nh);
+        }
         PG_CUDA(cudaMemcpyAsync(c->d_stage[buf], c->h_stage[buf], n + nh, cudaMemcpyHostToDevice, c->copy_stream));
       }
       PG_CUDA(cudaEventRecord(c->stage_ready[buf], c->copy_stream));
@@ -1054,8 +1152,14 @@ static int feed_finish(pg_counter* c) {
   PG_CUDA(cudaMemcpyAsync(sc, c->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
   PG_CUDA(cudaStreamSynchronize(c->stream));
   c->kmers_seen = sc[SC_KMERS];
+  c->last_probe_ms = 0.0;
+  for (int i = 0; i < c->n_probe; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev_probe[2 * i], c->ev_probe[2 * i + 1]) == cudaSuccess) c->last_probe_ms += ms;
+  }
   if (sc[SC_ERROR] & ERR_PROBE) return fail(PG_ERR_FULL, "k-mer table full: raise hash_size (-e)");
   if (sc[SC_ERROR] & ERR_HALO) return fail(PG_ERR_FORMAT, "sequence layout not supported: more than 97 line breaks inside one k-mer");
+  if (sc[SC_ERROR] & ERR_FASTQ) return fail(PG_ERR_FORMAT, "FASTQ file is not in the 4-line layout (wrapped sequence lines or blank lines): every record must be '@' header / sequence / '+' / quality");
   if (sc[SC_DISTINCT] > c->max_distinct)
     return fail(PG_ERR_FULL, "k-mer table over its design load: " + std::to_string(sc[SC_DISTINCT]) + " distinct k-mers > " + std::to_string(c->max_distinct) + "; raise hash_size (-e)");
   return PG_OK;
@@ -1091,23 +1195,17 @@ int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_le
   return PG_OK;
 }
 
-static bool read_file(const char* path, std::vector<char>& out, std::string& err) {
-  FILE* f = fopen(path, "rb");
-  if (!f) {
-    err = std::string("File ") + path + " cannot be opened.";
-    return false;
+// opens a sequence file for streaming; returns the descriptor (or -1) and its size
+static int open_sized(const char* path, uint64_t& size, std::string& err) {
+  const int fd = open(path, O_RDONLY);
+  struct stat st;
+  if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+    if (fd >= 0) close(fd);
+    err = std::string("File ") + path + " cannot be opened.";  // check_input_file, src/commands.cpp:42-49
+    return -1;
   }
-  fseek(f, 0, SEEK_END);
-  long long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  out.resize((size_t)sz);
-  size_t got = sz ? fread(out.data(), 1, (size_t)sz, f) : 0;
-  fclose(f);
-  if ((long long)got != sz) {
-    err = std::string("short read on ") + path;
-    return false;
-  }
-  return true;
+  size = (uint64_t)st.st_size;
+  return fd;
 }
 
 static bool ends_with(const std::string& s, const std::string& e) { return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0; }
@@ -1177,6 +1275,7 @@ extern "C" void pg_count_destroy(pg_counter* c) {
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->ev_p0) cudaEventDestroy(c->ev_p0);
   if (c->ev_p1) cudaEventDestroy(c->ev_p1);
+  for (cudaEvent_t ev : c->ev_probe) cudaEventDestroy(ev);
   for (int i = 0; i < pg_counter::NSTAGE; ++i) {
     if (c->d_stage[i]) cudaFree(c->d_stage[i]);
     if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -1238,13 +1337,42 @@ extern "C" pg_counter* pg_count_create(const char* reads_path, const char* segme
       return nullptr;
     }
   }
-  std::vector<char> reads, segs;
+  // both files are streamed: file -> ring of pinned staging buffers (pread) -> device, the copies running ahead of the
+  // counting kernels; nothing is held in host memory as a whole (a 30x human read set is ~185 GB, src/commands.cpp:829-833)
   std::string err;
-  if (!read_file(reads_path, reads, err) || (segments_path && !read_file(segments_path, segs, err))) {
+  uint64_t reads_len = 0, segs_len = 0;
+  const int rfd = open_sized(reads_path, reads_len, err);
+  const int sfd = rfd >= 0 && segments_path ? open_sized(segments_path, segs_len, err) : -1;
+  if (rfd < 0 || (segments_path && sfd < 0)) {
+    if (rfd >= 0) close(rfd);
     fail(PG_ERR_IO, err);
     return nullptr;
   }
-  return pg_count_create_from_buffers(reads.data(), reads.size(), segments_path ? segs.data() : nullptr, segs.size(), k, hash_size, device);
+  const uint64_t max_distinct = segments_path ? std::max<uint64_t>(segs_len, 1024) : std::max<uint64_t>(hash_size, 1024);
+  pg_counter* c = pg_count_new(k, max_distinct, device);
+  int st = c ? PG_OK : last_code();
+  if (c) {
+    DeviceGuard g(c->device);
+    if (segments_path) st = feed_enqueue(c, nullptr, segs_len, PG_OP_PRIME, c->ev_p0, c->ev_p1, nullptr, sfd);
+    if (st == PG_OK) st = feed_enqueue(c, nullptr, reads_len, segments_path ? PG_OP_UPDATE : PG_OP_COUNT, c->ev_t0, c->ev_t1, nullptr, rfd);
+    if (st == PG_OK) st = feed_finish(c);
+    if (st == PG_OK) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+      c->last_feed_ms = ms;
+    }
+  }
+  close(rfd);
+  if (sfd >= 0) close(sfd);
+  if (st != PG_OK) {
+    if (c) {
+      const std::string msg = pg_last_error();
+      pg_count_destroy(c);
+      fail(st, msg);
+    }
+    return nullptr;
+  }
+  return c;
 }
 
 static int lookup_codes(const pg_counter* c, const uint64_t* h_codes, uint64_t n, uint64_t* out) {
@@ -1317,6 +1445,7 @@ extern "C" int pg_count_histogram(const pg_counter* c, uint64_t max_count, uint6
   if (!c || !bins) return fail(PG_ERR_ARG, "null argument");
   DeviceGuard g(c->device);
   pg_counter* m = const_cast<pg_counter*>(c);  // scratch only; the table is not modified
+  std::lock_guard<std::mutex> lock(m->scratch_mutex);  // d_bins and the stream are shared by concurrent callers
   if (m->d_bins_cap < max_count + 1) {
     if (m->d_bins) cudaFree(m->d_bins);
     m->d_bins = nullptr;
@@ -1339,6 +1468,7 @@ extern "C" int pg_count_kmer_coverage(const pg_counter* c, uint64_t genome_kmers
   clear_error();
   if (!c || !out || genome_kmers == 0) return fail(PG_ERR_ARG, "invalid argument");
   DeviceGuard g(c->device);
+  std::lock_guard<std::mutex> lock(const_cast<pg_counter*>(c)->scratch_mutex);  // SC_COUNT_SUM is shared scratch
   cudaMemsetAsync(c->d_scalars + SC_COUNT_SUM, 0, 8, c->stream);
   count_sum_kernel<<<148 * 2, 512, 0, c->stream>>>(c->slots, c->capacity, c->d_scalars);
   count_launch();
@@ -1386,7 +1516,13 @@ extern "C" int pg_count_device_arrays(const pg_counter* c, uint64_t* slots_addr,
   if (!c) return fail(PG_ERR_ARG, "null counter");
   DeviceGuard g(c->device);
   pg_counter* m = const_cast<pg_counter*>(c);
-  if (counts_addr && !m->d_counts_tmp) PG_CUDA(cudaMalloc((void**)&m->d_counts_tmp, c->capacity * sizeof(uint32_t)));
+  if (counts_addr && m->counts_tmp_cap < c->capacity) {
+    if (m->d_counts_tmp) cudaFree(m->d_counts_tmp);
+    m->d_counts_tmp = nullptr;
+    m->counts_tmp_cap = 0;
+    PG_CUDA(cudaMalloc((void**)&m->d_counts_tmp, c->capacity * sizeof(uint32_t)));
+    m->counts_tmp_cap = c->capacity;
+  }
   if (slots_addr) *slots_addr = (uint64_t)(uintptr_t)c->slots;
   if (counts_addr) *counts_addr = (uint64_t)(uintptr_t)m->d_counts_tmp;
   if (capacity) *capacity = c->capacity;
@@ -1395,26 +1531,80 @@ extern "C" int pg_count_device_arrays(const pg_counter* c, uint64_t* slots_addr,
 
 extern "C" int pg_count_export_counts(pg_counter* c) {
   clear_error();
-  if (!c || !c->d_counts_tmp) return fail(PG_ERR_ARG, "call pg_count_device_arrays first");
+  if (!c || !c->d_counts_tmp || c->counts_tmp_cap < c->capacity) return fail(PG_ERR_ARG, "call pg_count_device_arrays first");
+  return pg_count_export_range(c, 0, c->capacity);
+}
+
+extern "C" int pg_count_import_counts(pg_counter* c) {
+  clear_error();
+  if (!c || !c->d_counts_tmp || c->counts_tmp_cap < c->capacity) return fail(PG_ERR_ARG, "call pg_count_device_arrays first");
+  return pg_count_import_range(c, 0, c->capacity);
+}
+
+extern "C" int pg_count_exchange_buffer(pg_counter* c, uint64_t n_slots, uint64_t* addr) {
+  clear_error();
+  if (!c || !addr || n_slots == 0 || (n_slots & 3)) return fail(PG_ERR_ARG, "invalid exchange buffer request");
   DeviceGuard g(c->device);
-  export_counts_kernel<<<148 * 4, 512, 0, c->stream>>>(c->slots, c->capacity, c->d_counts_tmp);
+  if (c->counts_tmp_cap < n_slots) {
+    if (c->d_counts_tmp) cudaFree(c->d_counts_tmp);
+    c->d_counts_tmp = nullptr;
+    c->counts_tmp_cap = 0;
+    PG_CUDA(cudaMalloc((void**)&c->d_counts_tmp, n_slots * sizeof(uint32_t)));
+    c->counts_tmp_cap = n_slots;
+  }
+  *addr = (uint64_t)(uintptr_t)c->d_counts_tmp;
+  return PG_OK;
+}
+
+static int range_args(const pg_counter* c, uint64_t first_slot, uint64_t n_slots) {
+  if (!c || !c->d_counts_tmp) return fail(PG_ERR_ARG, "call pg_count_exchange_buffer first");
+  if ((first_slot & 3) || (n_slots & 3) || first_slot + n_slots > c->capacity || n_slots > c->counts_tmp_cap)
+    return fail(PG_ERR_ARG, "slot range must be bucket aligned, inside the table and not larger than the exchange buffer");
+  return PG_OK;
+}
+
+extern "C" int pg_count_export_range(pg_counter* c, uint64_t first_slot, uint64_t n_slots) {
+  clear_error();
+  PG_TRY(range_args(c, first_slot, n_slots));
+  if (n_slots == 0) return PG_OK;
+  DeviceGuard g(c->device);
+  export_counts_kernel<<<148 * 4, 512, 0, c->stream>>>(c->slots, first_slot >> 2, n_slots >> 2, c->d_counts_tmp);
   count_launch();
   PG_CUDA(cudaStreamSynchronize(c->stream));
   return PG_OK;
 }
 
-extern "C" int pg_count_import_counts(pg_counter* c) {
+extern "C" int pg_count_import_range(pg_counter* c, uint64_t first_slot, uint64_t n_slots) {
   clear_error();
-  if (!c || !c->d_counts_tmp) return fail(PG_ERR_ARG, "call pg_count_device_arrays first");
+  PG_TRY(range_args(c, first_slot, n_slots));
+  if (n_slots == 0) return PG_OK;
   DeviceGuard g(c->device);
-  import_counts_kernel<<<148 * 4, 512, 0, c->stream>>>(c->slots, c->capacity, c->d_counts_tmp);
+  import_counts_kernel<<<148 * 4, 512, 0, c->stream>>>(c->slots, first_slot >> 2, n_slots >> 2, c->d_counts_tmp);
   count_launch();
   PG_CUDA(cudaStreamSynchronize(c->stream));
+  return PG_OK;
+}
+
+extern "C" int pg_count_canonicalize(pg_counter* c) {
+  clear_error();
+  if (!c) return fail(PG_ERR_ARG, "null counter");
+  DeviceGuard g(c->device);
+  canonicalize_kernel<<<148 * 8, 256, 0, c->stream>>>(c->slots, c->capacity >> 2, c->cap_q, c->cap_sh, c->d_scalars);
+  count_launch();
+  PG_CUDA(cudaGetLastError());
+  unsigned long long err = 0;
+  PG_CUDA(cudaMemcpyAsync(&err, c->d_scalars + SC_ERROR, 8, cudaMemcpyDeviceToHost, c->stream));
+  PG_CUDA(cudaStreamSynchronize(c->stream));
+  if (err & ERR_PROBE) return fail(PG_ERR_ARG, "canonicalize: the table is not a valid linear-probing layout");
   return PG_OK;
 }
 
 extern "C" uint64_t pg_count_kmers_seen(const pg_counter* c) { return c ? c->kmers_seen : 0; }
 extern "C" double pg_count_last_ms(const pg_counter* c) { return c ? c->last_feed_ms : 0.0; }
+extern "C" double pg_count_last_probe_ms(const pg_counter* c, uint32_t* n_passes) {
+  if (n_passes) *n_passes = c ? (uint32_t)c->n_probe : 0u;
+  return c ? c->last_probe_ms : 0.0;
+}
 
 extern "C" int pg_count_clear(pg_counter* c) {
   clear_error();

@@ -4,11 +4,11 @@ Chromosomes are independent HMM chains and reads are independent units, so:
   * chromosomes are assigned to ranks by LPT (longest processing time first) on their variant counts,
     mirroring the reference's descending-size job order (reference src/graphbuilder.cpp:273-276);
   * the read file is cut into record-aligned byte ranges, one per rank;
-  * rank 0 PRIMEs the k-mer table from the segment file and BROADCASTS the key array (one NCCL call), so every
-    rank holds a layout-identical table; every rank UPDATEs its read shard; the count arrays are ALL-REDUCED
-    (one NCCL call).  No other collective: histogram peak, fill, emission and forward-backward run per rank on
-    its own chromosomes.
-The device arrays are exposed by pg_count_device_arrays and wrapped zero-copy as torch tensors.
+  * every rank PRIMEs the k-mer table from the segment file itself and rewrites it into the canonical key layout
+    (pg_count_canonicalize: a function of the key SET only), so all ranks hold the identical table without a broadcast;
+    every rank UPDATEs its read shard; the count arrays are ALL-REDUCED - the one collective of the path.  Histogram peak,
+    fill, emission and forward-backward run per rank on its own chromosomes with no further exchange.
+The exchange buffer is exposed by pg_count_exchange_buffer and wrapped zero-copy as a torch tensor.
 """
 from __future__ import annotations
 
@@ -70,41 +70,58 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
-def counter_tensors(counter):
-    """(slots int64[2*cap], counts int32[cap]) torch views of a KmerCounter's device arrays (no copy).
-    `slots` is the table itself (16-byte slots); `counts` is the contiguous staging array of the all-reduce."""
+EXCHANGE_SLOTS = 1 << 28   # counts moved per all-reduce call (1 GiB of u32): large enough for full NVLink bus bandwidth
+
+
+def exchange_tensor(counter, n_slots: int):
+    """torch int32 view (no copy) of the counter's contiguous exchange buffer of `n_slots` counts."""
     import torch
-    sp, cp, cap = counter.device_arrays()
-    slots = torch.as_tensor(_CudaArray(sp, 2 * cap, "<i8"), device="cuda")
-    counts = torch.as_tensor(_CudaArray(cp, cap, "<i4"), device="cuda")
-    return slots, counts
+    addr = counter.exchange_buffer(n_slots)
+    return torch.as_tensor(_CudaArray(addr, n_slots, "<i4"), device="cuda")
 
 
-def sharded_count(counter, reads, segments, rank: int, world: int, group=None):
-    """PRIME on rank 0 + broadcast keys, UPDATE the local read shard, all-reduce counts.
+def allreduce_counts(counter, world: int, group=None, chunk_slots: int = EXCHANGE_SLOTS, view=None, sync=None):
+    """Adds the count arrays of all ranks position by position: THE collective of the sharded sample.
 
-    `reads` is this rank's record-aligned shard (host numpy / pinned torch / cuda torch uint8); `segments` is
-    only read on rank 0.  `counter` must have been created with the same max_distinct on every rank.
-    """
-    import torch
+    The counts live interleaved with the keys in 64-byte buckets, so they pass through a contiguous exchange buffer in
+    pieces of `chunk_slots` counts: export (device kernel) -> all-reduce (NCCL on torch's stream) -> import.  Every rank must
+    hold the canonical key layout (KmerCounter.canonicalize after PRIME).  `view` / `sync` are injection points for the
+    host-logic test (a numpy-backed counter and gloo)."""
     import torch.distributed as dist
+    if world <= 1:
+        return 0
+    cap = counter.capacity()
+    chunk = min(cap, max(4, chunk_slots & ~3))
+    buf = (view or exchange_tensor)(counter, chunk)
+    calls = 0
+    for first in range(0, cap, chunk):
+        n = min(chunk, cap - first)
+        counter.export_range(first, n)          # synchronises the counter's stream: the buffer is complete
+        dist.all_reduce(buf[:n], op=dist.ReduceOp.SUM, group=group)
+        if sync is not None:
+            sync()                               # NCCL runs on torch's stream: the sums must be complete before the import kernel
+        counter.import_range(first, n)
+        calls += 1
+    return calls
+
+
+def sharded_count(counter, reads, segments, rank: int, world: int, group=None, chunk_slots: int = EXCHANGE_SLOTS):
+    """Every rank PRIMEs the full segment file into its own table and brings it into the canonical layout (identical on
+    all ranks, no broadcast), UPDATEs with its own record-aligned shard of the reads, then the count arrays are summed
+    over the ranks by all-reduce.  `counter` must have been created with the same max_distinct on every rank.
+    Returns {"prime_ms", "update_ms", "allreduce_calls", "exchange_ms"}."""
+    import time
+
+    import torch
     from . import PG_OP_PRIME, PG_OP_UPDATE
-    slots, counts = counter_tensors(counter)
-    if rank == 0:
-        counter.feed(segments, PG_OP_PRIME)
-    on_gpu = slots.is_cuda
+    counter.feed(segments, PG_OP_PRIME)
+    prime_ms = counter.last_ms()
     if world > 1:
-        dist.broadcast(slots, src=0, group=group)
-        if on_gpu:
-            # NCCL runs on torch's stream, the counter on its own non-blocking stream: the keys must have
-            # arrived before the UPDATE kernels probe them
-            torch.cuda.current_stream().synchronize()
+        counter.canonicalize()
+    update_ms = 0.0
     if reads is not None and len(reads):
         counter.feed(reads, PG_OP_UPDATE)
-    if world > 1:
-        counter.export_counts()
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-        if on_gpu:
-            torch.cuda.current_stream().synchronize()  # the reduced counts must be complete before the import kernel
-        counter.import_counts()
-    return counter
+        update_ms = counter.last_ms()
+    t0 = time.perf_counter()   # export / import synchronise the counter's stream and `sync` torch's: host time = device time here
+    calls = allreduce_counts(counter, world, group, chunk_slots, sync=lambda: torch.cuda.current_stream().synchronize())
+    return {"prime_ms": prime_ms, "update_ms": update_ms, "allreduce_calls": calls, "exchange_ms": 1e3 * (time.perf_counter() - t0)}

@@ -141,6 +141,21 @@ class KmerCounter:
     def clear(self):
         _check(self._lib, self._lib.pg_count_clear(self._h))
 
+    def canonicalize(self):
+        """Deterministic key layout after PRIME (pg_count_canonicalize): identical on every GPU that primed the same file."""
+        _check(self._lib, self._lib.pg_count_canonicalize(self._h))
+
+    def exchange_buffer(self, n_slots: int) -> int:
+        a = C.c_uint64(0)
+        _check(self._lib, self._lib.pg_count_exchange_buffer(self._h, n_slots, C.byref(a)))
+        return a.value
+
+    def export_range(self, first_slot: int, n_slots: int):
+        _check(self._lib, self._lib.pg_count_export_range(self._h, first_slot, n_slots))
+
+    def import_range(self, first_slot: int, n_slots: int):
+        _check(self._lib, self._lib.pg_count_import_range(self._h, first_slot, n_slots))
+
     def distinct(self) -> int:
         return int(self._lib.pg_count_distinct(self._h))
 
@@ -152,6 +167,11 @@ class KmerCounter:
 
     def last_ms(self) -> float:
         return float(self._lib.pg_count_last_ms(self._h))
+
+    def last_probe_ms(self):
+        """(device ms spent in the probe passes of the last partitioned feed, number of passes)."""
+        n = C.c_uint32(0)
+        return float(self._lib.pg_count_last_probe_ms(self._h, C.byref(n))), int(n.value)
 
     def device_arrays(self):
         k, c, cap = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=3)
     args = ap.parse_args()
     import pangenie_b200 as pg
-    from pangenie_b200 import synth
+    from synthdata import small as synth
     from bench import fb_bytes_per_column, measured_peak_gbs
     peak_gbs, src = measured_peak_gbs()
     eng = pg.Engine(0)

@@ -16,7 +16,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .panel import Panel
+from pangenie_b200.panel import Panel
 
 GRCH38_AUTOSOME_MBP = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51]
 _ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)

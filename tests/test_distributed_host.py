@@ -11,8 +11,31 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pangenie_b200 import synth
-from pangenie_b200.distributed import lpt_assign, record_ranges
+from synthdata import small as synth
+from pangenie_b200.distributed import allreduce_counts, lpt_assign, record_ranges
+
+
+class _HostCounter:
+    """Stand-in for a device k-mer table in the host-logic test: counts interleaved with other data, moved through a
+    contiguous exchange buffer by ranges exactly like pg_count_export_range / pg_count_import_range."""
+
+    def __init__(self, counts: np.ndarray):
+        self.table = np.zeros((len(counts), 4), np.int32)
+        self.table[:, 2] = counts
+        self.buf = None
+
+    def capacity(self):
+        return self.table.shape[0]
+
+    def view(self, _counter, n):
+        self.buf = torch.zeros(n, dtype=torch.int32)
+        return self.buf
+
+    def export_range(self, first, n):
+        self.buf[:n] = torch.from_numpy(self.table[first:first + n, 2].copy())
+
+    def import_range(self, first, n):
+        self.table[first:first + n, 2] = self.buf[:n].numpy()
 
 
 def test_lpt_assign_balances_and_is_deterministic():
@@ -63,6 +86,14 @@ def _worker(rank, world, port, tmp):
         dist.all_reduce(local, op=dist.ReduceOp.SUM)
         full = oracles.OracleCounter(lib, wl.reads_fastq, wl.segments_fasta, wl.k)
         assert np.array_equal(local.numpy(), full.lookup(probes).astype(np.int64)), "sharded counts differ"
+        # the exchange itself: the count arrays of layout-identical tables summed range by range through the exchange
+        # buffer (capacity not a multiple of the chunk, several calls)
+        rng = np.random.default_rng(100 + rank)
+        mine_counts = rng.integers(0, 50, size=1000 + 4 * 7).astype(np.int32)
+        hc = _HostCounter(mine_counts)
+        calls = allreduce_counts(hc, world, chunk_slots=256, view=hc.view)
+        want = sum(np.random.default_rng(100 + r).integers(0, 50, size=1000 + 4 * 7).astype(np.int32) for r in range(world))
+        assert calls == 5 and np.array_equal(hc.table[:, 2], want) and not hc.table[:, [0, 1, 3]].any()
         # chromosome assignment: every chromosome genotyped exactly once across ranks
         mine = lpt_assign([p.n_variants for p in wl.panels], world)[rank]
         got = [None] * world

@@ -210,7 +210,7 @@ def test_empty_and_degenerate_inputs(engine, oracle):
 def test_full_size_properties(engine):
     """cfg-scale shape (H=64) without an oracle: rows are normalised, GT is the argmax, results are
     reproducible and independent of how chromosomes are batched."""
-    from pangenie_b200 import synth
+    from synthdata import small as synth
     wl = synth.make_workload(n_chrom=3, n_variants=6000, n_haplotypes=64, coverage=0, with_reads=False, seed=4)
     synth.fill_synthetic_counts(np.random.default_rng(4), wl)
     table = pg.ProbabilityTable(6, 96, 48, 0.01)

@@ -16,7 +16,7 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         import pangenie_b200 as pg
-        from pangenie_b200 import synth
+        from synthdata import small as synth
         from pangenie_b200.distributed import lpt_assign, record_ranges, sharded_count
         wl = synth.make_workload(n_chrom=4, n_variants=1600, n_haplotypes=8, coverage=8.0, seed=31)
         mine = lpt_assign([p.n_variants for p in wl.panels], world)[rank]
@@ -40,7 +40,7 @@ def test_two_gpu_sharded_run_matches_single_gpu(tmp_path, engine):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
-    from pangenie_b200 import synth
+    from synthdata import small as synth
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import pangenie_b200 as pg
-from pangenie_b200 import synth
+from synthdata import small as synth
 from tests import oracles
 from tests.helpers import assert_results_close
 
