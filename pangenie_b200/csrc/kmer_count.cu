@@ -511,11 +511,17 @@ __device__ __noinline__ void probe1(uint64_t kmer, const TableRef& T, uint32_t& 
 // key and a 4-byte count).  With partitioning the tile kernel does not probe: it appends each canonical k-mer to the
 // buffer of the table partition its home bucket lies in (streaming 8-byte writes), and probe_parts_kernel then works
 // through the partitions one after the other, so the slice of the table being hit (<= ~24 MB) stays L2-resident.
-constexpr int MAX_PARTS = 255;
+// Every partition is split into PART_REPL regions, one per residue class of the tile index: the region cursors are the only
+// global atomics of the scatter pass, and with one cursor per partition ALL tiles hammered the same few L2 lines (measured
+// on configs[2], 230 partitions: the pass ran at 113 GB/s of text against 267 GB/s with 23 partitions).  Cursors sit
+// CURSOR_STRIDE words apart (one 128-byte line each) so they spread over the L2 slices.
+constexpr int MAX_PARTS = 1023;
+constexpr int PART_REPL = 16;
+constexpr int CURSOR_STRIDE = 32;
 struct PartArgs {
-  uint64_t* buf;         // [n_parts][region_cap] canonical k-mers
-  uint32_t* cursor;      // [n_parts] k-mers appended (may run past region_cap: the excess was probed directly)
-  uint32_t* work;        // probe_parts_kernel work-item counter
+  uint64_t* buf;          // [n_parts * PART_REPL][region_cap] canonical k-mers
+  uint32_t* cursor;       // [n_parts * PART_REPL * CURSOR_STRIDE] k-mers appended (may run past region_cap: the excess was probed directly)
+  uint32_t* item_start;   // [n_parts * PART_REPL + 1] first probe item of every region (part_items_kernel)
   uint32_t region_cap;
   uint32_t n_parts;
 };
@@ -523,6 +529,7 @@ __device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
   return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
 }
 
+constexpr size_t SCATTER_SMEM = (size_t)(MAX_PARTS + 1) * 4 + (size_t)CT_TILE * 4 + (size_t)CT_TILE * 8;  // s_cnt + s_info + s_kmer
 constexpr int PK_WORDS = CT_TILE / 16 + 4;  // packed codes: 16 symbols per word (+ read-ahead padding)
 constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per word
 
@@ -538,8 +545,12 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   __shared__ uint32_t s_nb[NB_WORDS];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
-  __shared__ uint32_t s_cnt[SCATTER ? MAX_PARTS + 1 : 1];   // k-mers of this tile per partition, then write cursors
-  __shared__ uint8_t s_part[SCATTER ? CT_TILE : 1];         // partition of the k-mer starting at each symbol (255: none)
+  // scatter mode (dynamic shared memory, 52 KB): per-partition counts -> write cursors, (partition, rank) and the canonical
+  // k-mer of every start position, so each k-mer costs ONE shared-memory atomic and is extracted once
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_dyn);                                            // [MAX_PARTS + 1]
+  uint32_t* s_info = s_cnt + (MAX_PARTS + 1);                                                      // [CT_TILE]
+  unsigned long long* s_kmer = reinterpret_cast<unsigned long long*>(s_info + CT_TILE);            // [CT_TILE]
   unsigned long long* scalars = T.scalars;
   if (SCATTER)
     for (int i = threadIdx.x; i <= MAX_PARTS; i += CT_THREADS) s_cnt[i] = 0;
@@ -613,9 +624,12 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     uint32_t state;
     if (last_before >= 0) {
       if (last_before + 1 == tid * 16) state = LS_LINE_START;
-      else state = text[base + last_before + 1] == '>' ? LS_HEADER : LS_SEQ;
+      else state = (base + last_before + 1 < n_avail && text[base + last_before + 1] == '>') ? LS_HEADER : LS_SEQ;
     } else {
+      // no newline before my bytes in this tile: I am still in the line the tile starts in.  If the tile starts exactly at a
+      // line start, only thread 0 sees that line's first byte; everybody else takes the state that byte decides
       state = (meta >> 2) & 3u;
+      if (state == LS_LINE_START && tid > 0) state = text[base] == '>' ? LS_HEADER : LS_SEQ;
     }
     uint32_t rest = nlbits, start = 0;
 #pragma unroll 1
@@ -699,33 +713,36 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
       probeN<OP, false, 4>(cn, vm, T, inserted, nullptr);
     }
   } else {
-    // (1) count my k-mers per partition, (2) reserve one contiguous range per partition for the whole tile,
-    // (3) append.  A partition region that is full (skewed data) sends its k-mers straight to the table.
+    // (1) rank my k-mers within their partition (the shared-memory atomic returns the rank), (2) reserve one contiguous
+    // range per partition for the whole tile in this tile's replica region, (3) append.  A region that is full (skewed
+    // data) sends its k-mers straight to the table.
+    const uint32_t repl = blockIdx.x % PART_REPL;
 #pragma unroll 1
     for (uint32_t p = (uint32_t)tid; p < n_owned_syms; p += CT_THREADS) {
       uint64_t can;
-      uint32_t part = 255u;
+      uint32_t info = 0xffffffffu;
       if (kmer_at(p, can)) {
-        part = part_of(can, pa.n_parts);
-        atomicAdd(&s_cnt[part], 1u);
+        const uint32_t part = part_of(can, pa.n_parts);
+        info = (part << 12) | atomicAdd(&s_cnt[part], 1u);   // rank < 4096 = CT_TILE
+        s_kmer[p] = can;
         ++nk;
       }
-      s_part[p] = (uint8_t)part;
+      s_info[p] = info;
     }
     __syncthreads();
     for (uint32_t q = (uint32_t)tid; q < pa.n_parts; q += CT_THREADS) {
       const uint32_t cnt = s_cnt[q];
-      s_cnt[q] = cnt ? atomicAdd(pa.cursor + q, cnt) : 0u;
+      s_cnt[q] = cnt ? atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cnt) : 0u;
     }
     __syncthreads();
 #pragma unroll 1
     for (uint32_t p = (uint32_t)tid; p < n_owned_syms; p += CT_THREADS) {
-      const uint32_t part = s_part[p];
-      if (part != 255u) {
-        uint64_t can;
-        kmer_at(p, can);
-        const uint32_t pos = atomicAdd(&s_cnt[part], 1u);
-        if (pos < pa.region_cap) pa.buf[(size_t)part * pa.region_cap + pos] = can;
+      const uint32_t info = s_info[p];
+      if (info != 0xffffffffu) {
+        const uint32_t part = info >> 12;
+        const uint32_t pos = s_cnt[part] + (info & 0xfffu);
+        const uint64_t can = s_kmer[p];
+        if (pos < pa.region_cap) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + (size_t)(part * PART_REPL + repl) * pa.region_cap + pos), can);
         else probe1<OP>(can, T, inserted);
       }
     }
@@ -746,34 +763,50 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 constexpr int PP_ITEM = 8192;
 constexpr bool PP_QUEUE = false;  // park overflow walks in a shared-memory queue (barriers per item) or walk in place
 constexpr int PP_BATCH = 4;  // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
+// item_start[r] = first probe item of region r (exclusive scan of ceil(fill / PP_ITEM) over the regions); one CTA
+__global__ void __launch_bounds__(1024) part_items_kernel(const PartArgs pa) {
+  __shared__ uint32_t s_sum[1024];
+  const uint32_t n_regions = pa.n_parts * PART_REPL;
+  const uint32_t per = (n_regions + 1023) / 1024;
+  const uint32_t r0 = threadIdx.x * per, r1 = min(r0 + per, n_regions);
+  uint32_t sum = 0;
+  for (uint32_t r = r0; r < r1; ++r) sum += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + PP_ITEM - 1) / PP_ITEM;
+  s_sum[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t a = (int)threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s_sum[threadIdx.x] += a;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? s_sum[threadIdx.x - 1] : 0u;
+  for (uint32_t r = r0; r < r1; ++r) {
+    pa.item_start[r] = run;
+    run += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + PP_ITEM - 1) / PP_ITEM;
+  }
+  if (threadIdx.x == 1023) pa.item_start[n_regions] = s_sum[1023];
+}
+
 template <int OP>
 __global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, const TableRef T) {
-  __shared__ uint32_t s_start[MAX_PARTS + 2];  // first item of each partition
   __shared__ WalkQueue s_wq;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    uint32_t run = 0;
-    for (uint32_t q = 0; q < pa.n_parts; ++q) {
-      s_start[q] = run;
-      const uint32_t nq = min(pa.cursor[q], pa.region_cap);
-      run += (nq + PP_ITEM - 1) / PP_ITEM;
-    }
-    s_start[pa.n_parts] = run;
-    s_wq.n = 0;
-  }
+  if (tid == 0) s_wq.n = 0;
   __syncthreads();
-  const uint32_t total = s_start[pa.n_parts];
+  const uint32_t n_regions = pa.n_parts * PART_REPL;
+  const uint32_t* __restrict__ s_start = pa.item_start;  // regions in partition order (part_items_kernel)
+  const uint32_t total = s_start[n_regions];
   uint32_t inserted = 0;
   // items are dealt round-robin: the CTAs running at any moment work on neighbouring items = the same table slice
   for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
-    uint32_t lo = 0, hi = pa.n_parts;  // largest q with s_start[q] <= item
+    uint32_t lo = 0, hi = n_regions;  // largest q with s_start[q] <= item (regions without items share their successor's start)
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
       if (s_start[mid] <= item) lo = mid;
       else hi = mid;
     }
     const uint32_t q = lo;
-    const uint32_t nq = min(pa.cursor[q], pa.region_cap);
+    const uint32_t nq = min(pa.cursor[(size_t)q * CURSOR_STRIDE], pa.region_cap);
     const uint32_t off = (item - s_start[q]) * PP_ITEM;
     const uint64_t* src = pa.buf + (size_t)q * pa.region_cap + off;
     const uint32_t m = min((uint32_t)PP_ITEM, nq - off);
@@ -978,8 +1011,14 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
   PartArgs none;
   memset(&none, 0, sizeof(none));
   if (pa) {
-    if (op == PG_OP_COUNT) count_tile_kernel<PG_OP_COUNT, true><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
-    else count_tile_kernel<PG_OP_UPDATE, true><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
+    static bool attr_set[64] = {};   // per device
+    if (c->device < 64 && !attr_set[c->device]) {
+      PG_CUDA(cudaFuncSetAttribute(count_tile_kernel<PG_OP_COUNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
+      PG_CUDA(cudaFuncSetAttribute(count_tile_kernel<PG_OP_UPDATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
+      attr_set[c->device] = true;
+    }
+    if (op == PG_OP_COUNT) count_tile_kernel<PG_OP_COUNT, true><<<n_tiles, CT_THREADS, SCATTER_SMEM, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
+    else count_tile_kernel<PG_OP_UPDATE, true><<<n_tiles, CT_THREADS, SCATTER_SMEM, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
   } else {
     switch (op) {
       case PG_OP_COUNT: count_tile_kernel<PG_OP_COUNT, false><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, none); break;
@@ -993,14 +1032,16 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
 }
 
 // ---- partitioned counting: geometry and the probe pass over the filled buffers ----
-// text bytes scattered before the partition buffers are worked off (PG_COUNT_SUPER_MB: test knob)
-static uint64_t super_bytes() { return std::max<uint64_t>(env_u64("PG_COUNT_SUPER_MB", 1024), 1) << 20; }
-// tuning / test knobs: PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
-// PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning
+// Every probe pass sweeps the whole table through the L2 once (64 B read + 32 B write-back per touched bucket), so the
+// more text is scattered before a pass the fewer sweeps a file costs: the super-chunk is as large as the k-mer buffers
+// allow.  Knobs: PG_COUNT_SUPER_MB caps the text per pass (test knob), PG_COUNT_PART_BUF_MB the buffer memory (default: a
+// third of the free HBM, at most 24 GiB), PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
+// PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning.
 static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 96u << 10) << 10; }
+constexpr size_t PART_CURSOR_WORDS = (size_t)MAX_PARTS * PART_REPL * CURSOR_STRIDE;
 
-// decides whether this pass is partitioned; sizes the buffers for a super-chunk of `super` text bytes
-static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, PartArgs& pa, bool& use) {
+// decides whether this pass is partitioned; sizes the buffers; `super` = text bytes per probe pass
+static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is_fastq, PartArgs& pa, bool& use, uint64_t& super) {
   use = false;
   // text streamed over PCIe arrives slower than the direct kernel counts it: partitioning would only add a tail
   if (!resident && !env_u64("PG_COUNT_PART_STAGED", 0)) return PG_OK;
@@ -1008,10 +1049,25 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, PartAr
   const uint64_t table_bytes = (c->capacity >> 2) * sizeof(KmerBucket);
   if (op == PG_OP_PRIME || slice == 0 || table_bytes <= 2 * slice || len < env_u64("PG_COUNT_PART_MIN_TEXT", 4u << 20)) return PG_OK;
   const uint32_t n_parts = (uint32_t)std::min<uint64_t>(MAX_PARTS, (table_bytes + slice - 1) / slice);
-  const uint64_t super = std::min<uint64_t>(len, super_bytes());
-  // every text byte starts at most one k-mer; 1.5x the mean share per partition, the excess is probed directly
-  const uint64_t region = ((super + super / 2) / n_parts + 8192) & ~(uint64_t)15;
-  const uint64_t need = region * n_parts;
+  const uint64_t n_regions = (uint64_t)n_parts * PART_REPL;
+  // k-mers per text byte: at most 1 (FASTA); a FASTQ record spends more than half of its bytes on header and qualities
+  const double density = is_fastq ? 0.5 : 1.0, slack = 1.25;
+  uint64_t budget = env_u64("PG_COUNT_PART_BUF_MB", 0) << 20;
+  if (!budget) {
+    size_t free_b = 0, total_b = 0;
+    PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    budget = std::min<uint64_t>(24ull << 30, (uint64_t)(free_b + c->part_buf_cap * 8) / 3);
+  }
+  uint64_t want_super = std::min<uint64_t>(len, env_u64("PG_COUNT_SUPER_MB", 1ull << 30) << 20);
+  uint64_t kcap = (uint64_t)((double)want_super * density * slack) + n_regions * 4096;   // k-mers the buffers should hold
+  if (c->part_buf_cap >= kcap) {
+    kcap = c->part_buf_cap;                       // buffers of an earlier pass are large enough: keep them
+  } else {
+    kcap = std::min<uint64_t>(kcap, std::max<uint64_t>(budget / 8, c->part_buf_cap));
+    kcap = std::max<uint64_t>(kcap, n_regions * 8192);
+  }
+  const uint64_t region = std::min<uint64_t>((kcap / n_regions) & ~(uint64_t)15, 0xfffffff0ull);
+  const uint64_t need = region * n_regions;
   if (c->part_buf_cap < need) {
     if (c->d_part_buf) cudaFree(c->d_part_buf);
     c->d_part_buf = nullptr;
@@ -1019,12 +1075,19 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, PartAr
     PG_CUDA(cudaMalloc((void**)&c->d_part_buf, need * 8));
     c->part_buf_cap = need;
   }
-  if (!c->d_part_cursor) PG_CUDA(cudaMalloc((void**)&c->d_part_cursor, 256 * sizeof(uint32_t)));
+  if (!c->d_part_cursor) {
+    PG_CUDA(cudaMalloc((void**)&c->d_part_cursor, (PART_CURSOR_WORDS + (size_t)MAX_PARTS * PART_REPL + 16) * sizeof(uint32_t)));
+    PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, PART_CURSOR_WORDS * sizeof(uint32_t), c->stream));
+  }
   pa.buf = reinterpret_cast<uint64_t*>(c->d_part_buf);
   pa.cursor = c->d_part_cursor;
-  pa.work = c->d_part_cursor + 255;
-  pa.region_cap = (uint32_t)std::min<uint64_t>(region, 0xfffffff0u);
+  pa.item_start = c->d_part_cursor + PART_CURSOR_WORDS;
+  pa.region_cap = (uint32_t)region;
   pa.n_parts = n_parts;
+  // text per pass the regions are sized for (the excess of an over-full region is probed directly, so an underestimate
+  // of the k-mer density costs speed, not correctness)
+  super = std::max<uint64_t>((uint64_t)((double)(region * n_regions) / (density * slack)), 1ull << 20);
+  super = std::min<uint64_t>(super, want_super);
   use = true;
   return PG_OK;
 }
@@ -1043,15 +1106,16 @@ static int part_flush(pg_counter* c, const PartArgs& pa, int op) {
     }
     PG_CUDA(cudaEventRecord(c->ev_probe[2 * c->n_probe], c->stream));
   }
+  part_items_kernel<<<1, 1024, 0, c->stream>>>(pa);
   if (op == PG_OP_COUNT) probe_parts_kernel<PG_OP_COUNT><<<sms * 6, 256, 0, c->stream>>>(pa, T);
   else probe_parts_kernel<PG_OP_UPDATE><<<sms * 6, 256, 0, c->stream>>>(pa, T);
-  count_launch();
+  count_launch(2);
   PG_CUDA(cudaGetLastError());
   if (timed) {
     PG_CUDA(cudaEventRecord(c->ev_probe[2 * c->n_probe + 1], c->stream));
     ++c->n_probe;
   }
-  PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, 256 * sizeof(uint32_t), c->stream));
+  PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (size_t)pa.n_parts * PART_REPL * CURSOR_STRIDE * sizeof(uint32_t), c->stream));
   return PG_OK;
 }
 
@@ -1095,9 +1159,10 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   PartArgs pa;
   memset(&pa, 0, sizeof(pa));
   bool parted = false;
-  PG_TRY(part_setup(c, len, op, direct, pa, parted));
-  if (parted) step = std::min<uint64_t>(step, super_bytes());  // a chunk never exceeds what the regions are sized for
-  if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, 256 * sizeof(uint32_t), c->stream));
+  uint64_t super = 0;
+  PG_TRY(part_setup(c, len, op, direct, is_fastq, pa, parted, super));
+  if (parted) step = std::min<uint64_t>(step, super);  // a chunk never exceeds what the regions are sized for
+  if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (size_t)pa.n_parts * PART_REPL * CURSOR_STRIDE * sizeof(uint32_t), c->stream));
   uint64_t scattered = 0;  // text bytes scattered into the partition buffers since the last flush
   for (uint64_t off = 0; off < len; off += step) {
     const uint64_t n = std::min<uint64_t>(step, len - off);
@@ -1137,7 +1202,7 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
     if (after_first_chunk && off == 0) PG_TRY((*after_first_chunk)());  // host work that overlaps the copies in flight
     if (parted) {
       scattered += n;
-      if (off + step >= len || scattered + step > super_bytes()) {  // the buffers are sized for super_bytes() of text
+      if (off + step >= len || scattered + step > super) {  // the buffers are sized for `super` bytes of text
         PG_TRY(part_flush(c, pa, op));
         scattered = 0;
       }

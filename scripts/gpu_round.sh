@@ -27,6 +27,17 @@ ncu)
   PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on \
      -k regex:"count_tile_kernel|probe_parts|block_kernel|skeleton_kernel" -s ${SKIP:-40} -c ${CNT:-8} -o $out/prof_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3s} > $out/ncu_$tag.out 2>&1; tail -3 $out/ncu_$tag.out;;
+ncu_probe)
+  PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"probe_parts" -s 1 -c 2 -o $out/prof_probe_$tag \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3} > $out/ncu_probe_$tag.out 2>&1; tail -3 $out/ncu_probe_$tag.out;;
+ncu_scatter)
+  PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"count_tile_kernel" -s 30 -c 2 -o $out/prof_scatter_$tag \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3} > $out/ncu_scatter_$tag.out 2>&1; tail -3 $out/ncu_scatter_$tag.out;;
+hmm_lean)
+  for lean in 0 1; do
+    PG_SKELETON_LEAN=$lean timeout 900 python scripts/bench_hmm.py --haplotypes 32 64 --variants 400000 --repeat 2 > $out/bench_hmm_lean${lean}_$tag.jsonl 2> $out/bench_hmm_lean${lean}_$tag.err
+    cat $out/bench_hmm_lean${lean}_$tag.jsonl; tail -2 $out/bench_hmm_lean${lean}_$tag.err
+  done;;
 ncu_hmm)
   PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"skeleton_kernel|block_kernel" -s 1 -c 2 -o $out/prof_hmm_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3s} > $out/ncu_hmm_$tag.out 2>&1; tail -3 $out/ncu_hmm_$tag.out;;
