@@ -321,6 +321,25 @@ int pg_engine_fetch(pg_engine* e, uint32_t n_chrom, pg_panel* panels, pg_hmm_res
 int pg_engine_run_counted(pg_engine* e, const pg_counter* c, int largest_peak, double regularization,
                           const pg_hmm_params* params, uint64_t* kmer_abundance_peak);
 
+/* ------------------------------------------------------------------------------------------------
+ * HaplotypeSampler - `HaplotypeSampler(&unique_kmers, size, recombrate, effective_N, &best_scores,
+ * add_reference, "", chromosome, allele_penalty)` (src/haplotypesampler.cpp:20-78), what fill_read_kmercounts runs on every
+ * chromosome when the panel has more than 100 paths (src/commands.cpp:139-146, 800-803): `size` integer Viterbi passes over the
+ * paths (costs: SamplingEmissions, src/samplingemissions.cpp:9-44; SamplingTransitions, src/samplingtransitions.cpp:5-22),
+ * each masking the cells and penalising the alleles of the passes before it, then the panel restricted to the sampled paths
+ * (update_unique_kmers, :289-303).  The panel must carry the filled kmer_counts.  n_out = size + (add_reference ? 1 : 0).
+ *   sampled_paths       [n_out][V]  path id chosen by pass i at every variant (get_sampled_paths(); the last row is the
+ *                                   reference path 0 if add_reference)
+ *   best_scores         [size]      Viterbi score of every pass
+ *   new_path_to_allele  [V][n_out]  alleles of the sampled paths = path_to_allele of the sampled panel
+ *   new_kmer_count      [V]         unique k-mers that still lie on a remaining allele; new_counts: their read counts,
+ *                                   concatenated in variant order
+ * Integer arithmetic throughout: identical to the reference, ties included.  Up to 1024 paths.
+ * ---------------------------------------------------------------------------------------------- */
+int pg_haplotype_sample(int device, const pg_panel* panel, uint32_t size, double recombrate, double effective_N,
+                        int add_reference, uint16_t allele_penalty, uint64_t* sampled_paths, uint32_t* best_scores,
+                        uint16_t* new_path_to_allele, uint32_t* new_kmer_count, uint16_t* new_counts);
+
 /** Empties a counter (all keys removed, counts zero) so its HBM allocation can be reused. */
 int pg_count_clear(pg_counter* c);
 

@@ -115,7 +115,7 @@ EXPORTS = [
     "pg_result_layout", "pg_engine_create", "pg_engine_destroy", "pg_hmm_run", "pg_emission_run",
     "pg_fill_counts", "pg_genotype_run", "pg_engine_timings",
     "pg_count_device_arrays", "pg_count_export_counts", "pg_count_import_counts", "pg_count_kmers_seen", "pg_count_last_ms", "pg_count_clear",
-    "pg_count_canonicalize", "pg_count_exchange_buffer", "pg_count_export_range", "pg_count_import_range",
+    "pg_count_canonicalize", "pg_count_exchange_buffer", "pg_count_export_range", "pg_count_import_range", "pg_haplotype_sample",
     "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted", "pg_hmm_run_subsets",
     "pg_index_open", "pg_index_open_archive", "pg_index_close", "pg_index_kmer_size", "pg_index_n_chromosomes",
     "pg_index_chromosome_name", "pg_index_add_reference", "pg_index_segments_path", "pg_index_panel",
@@ -202,6 +202,7 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "engine_run_resident", i32, [vp, vp, u64, vp, u64, u32, u64, dbl, C.POINTER(PgHmmParams), C.POINTER(u64)])
         _sig(lib, p + "engine_fetch", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgHmmResult)])
         _sig(lib, p + "engine_run_counted", i32, [vp, vp, i32, dbl, C.POINTER(PgHmmParams), C.POINTER(u64)])
+        _sig(lib, p + "haplotype_sample", i32, [i32, C.POINTER(PgPanel), u32, dbl, dbl, i32, C.c_uint16, vp, vp, vp, vp, vp])
         _sig(lib, p + "genotype_run", i32, [vp, C.POINTER(PgGenotypeInput), u32, C.POINTER(PgPanel), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult), C.POINTER(u64)])
     else:
         # oracles: same data arguments, no engine handle

@@ -515,7 +515,7 @@ __device__ __noinline__ void probe1(uint64_t kmer, const TableRef& T, uint32_t& 
 // global atomics of the scatter pass, and with one cursor per partition ALL tiles hammered the same few L2 lines (measured
 // on configs[2], 230 partitions: the pass ran at 113 GB/s of text against 267 GB/s with 23 partitions).  Cursors sit
 // CURSOR_STRIDE words apart (one 128-byte line each) so they spread over the L2 slices.
-constexpr int MAX_PARTS = 1023;
+constexpr int MAX_PARTS = 4095;
 constexpr int PART_REPL = 16;
 constexpr int CURSOR_STRIDE = 32;
 struct PartArgs {
@@ -553,7 +553,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   unsigned long long* s_kmer = reinterpret_cast<unsigned long long*>(s_info + CT_TILE);            // [CT_TILE]
   unsigned long long* scalars = T.scalars;
   if (SCATTER)
-    for (int i = threadIdx.x; i <= MAX_PARTS; i += CT_THREADS) s_cnt[i] = 0;
+    for (uint32_t i = threadIdx.x; i < pa.n_parts; i += CT_THREADS) s_cnt[i] = 0;
 
   const int tid = threadIdx.x;
   const uint64_t base = (uint64_t)blockIdx.x * CT_ADV;
@@ -716,34 +716,80 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     // (1) rank my k-mers within their partition (the shared-memory atomic returns the rank), (2) reserve one contiguous
     // range per partition for the whole tile in this tile's replica region, (3) append.  A region that is full (skewed
     // data) sends its k-mers straight to the table.
+    // Four start positions per thread and round: the passes are chains of dependent shared-memory operations (measured:
+    // 38% of the stall samples on the short scoreboard with one position in flight), so the loads / atomics of four
+    // independent positions are issued together.
     const uint32_t repl = blockIdx.x % PART_REPL;
+    constexpr int SB = 4;
 #pragma unroll 1
-    for (uint32_t p = (uint32_t)tid; p < n_owned_syms; p += CT_THREADS) {
-      uint64_t can;
-      uint32_t info = 0xffffffffu;
-      if (kmer_at(p, can)) {
-        const uint32_t part = part_of(can, pa.n_parts);
-        info = (part << 12) | atomicAdd(&s_cnt[part], 1u);   // rank < 4096 = CT_TILE
-        s_kmer[p] = can;
-        ++nk;
+    for (uint32_t p0 = (uint32_t)tid; p0 < n_owned_syms; p0 += SB * CT_THREADS) {
+      uint64_t can[SB];
+      uint32_t part[SB], rank[SB];
+      bool ok[SB];
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
+        ok[u] = kmer_at(min(p, n_owned_syms - 1u), can[u]) && p < n_owned_syms;   // (clamped: no reads past the packed stream)
+        part[u] = part_of(can[u], pa.n_parts);
       }
-      s_info[p] = info;
+#pragma unroll
+      for (int u = 0; u < SB; ++u) rank[u] = ok[u] ? atomicAdd(&s_cnt[part[u]], 1u) : 0u;   // rank < 4096 = CT_TILE
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
+        if (p < n_owned_syms) {
+          s_info[p] = ok[u] ? ((part[u] << 12) | rank[u]) : 0xffffffffu;
+          if (ok[u]) s_kmer[p] = can[u];
+        }
+        nk += ok[u] ? 1u : 0u;
+      }
     }
     __syncthreads();
-    for (uint32_t q = (uint32_t)tid; q < pa.n_parts; q += CT_THREADS) {
-      const uint32_t cnt = s_cnt[q];
-      s_cnt[q] = cnt ? atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cnt) : 0u;
+    {
+      // one reservation per non-empty partition; all atomics of a thread are in flight together
+      constexpr int QMAX = (MAX_PARTS + CT_THREADS) / CT_THREADS;
+      const int nq = (int)((pa.n_parts + CT_THREADS - 1) / CT_THREADS);
+      uint32_t basev[QMAX];
+#pragma unroll
+      for (int u = 0; u < QMAX; ++u) {
+        const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
+        basev[u] = 0;
+        if (u < nq && q < pa.n_parts) {
+          const uint32_t cnt = s_cnt[q];
+          if (cnt) basev[u] = atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cnt);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < QMAX; ++u) {
+        const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
+        if (u < nq && q < pa.n_parts) s_cnt[q] = basev[u];
+      }
     }
     __syncthreads();
 #pragma unroll 1
-    for (uint32_t p = (uint32_t)tid; p < n_owned_syms; p += CT_THREADS) {
-      const uint32_t info = s_info[p];
-      if (info != 0xffffffffu) {
-        const uint32_t part = info >> 12;
-        const uint32_t pos = s_cnt[part] + (info & 0xfffu);
-        const uint64_t can = s_kmer[p];
-        if (pos < pa.region_cap) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + (size_t)(part * PART_REPL + repl) * pa.region_cap + pos), can);
-        else probe1<OP>(can, T, inserted);
+    for (uint32_t p0 = (uint32_t)tid; p0 < n_owned_syms; p0 += SB * CT_THREADS) {
+      uint32_t info[SB], base[SB];
+      uint64_t can[SB];
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
+        info[u] = p < n_owned_syms ? s_info[p] : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
+        const bool ok = info[u] != 0xffffffffu;
+        base[u] = ok ? s_cnt[info[u] >> 12] : 0u;
+        can[u] = ok ? s_kmer[p] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        if (info[u] != 0xffffffffu) {
+          const uint32_t part = info[u] >> 12;
+          const uint32_t pos = base[u] + (info[u] & 0xfffu);
+          if (pos < pa.region_cap) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + (size_t)(part * PART_REPL + repl) * pa.region_cap + pos), can[u]);
+          else probe1<OP>(can[u], T, inserted);
+        }
       }
     }
   }
@@ -1037,7 +1083,7 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
 // allow.  Knobs: PG_COUNT_SUPER_MB caps the text per pass (test knob), PG_COUNT_PART_BUF_MB the buffer memory (default: a
 // third of the free HBM, at most 24 GiB), PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
 // PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning.
-static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 96u << 10) << 10; }
+static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 40u << 10) << 10; }
 constexpr size_t PART_CURSOR_WORDS = (size_t)MAX_PARTS * PART_REPL * CURSOR_STRIDE;
 
 // decides whether this pass is partitioned; sizes the buffers; `super` = text bytes per probe pass

@@ -341,6 +341,24 @@ class Engine:
             pass
 
 
+def haplotype_sample(panel: Panel, size: int, recombrate: float = 1.26, effective_N: float = 25000.0, add_reference: bool = False,
+                     allele_penalty: int = 10, device: int = 0):
+    """HaplotypeSampler(&unique_kmers, size, recombrate, effective_N, &best_scores, add_reference, "", chromosome,
+    allele_penalty) (src/haplotypesampler.cpp:20-78) on the device -> (sampled_paths [n_out, V], best_scores [size],
+    new_path_to_allele [V, n_out], new_kmer_count [V], new_counts)."""
+    lib = capi.load()
+    V, n_out = panel.n_variants, size + (1 if add_reference else 0)
+    paths = np.zeros((n_out, V), np.uint64)
+    scores = np.zeros(size, np.uint32)
+    p2a = np.zeros((V, n_out), np.uint16)
+    nk = np.zeros(V, np.uint32)
+    counts = np.zeros(max(len(panel.kmer_counts), 1), np.uint16)
+    ps = panel.as_struct()
+    _check(lib, lib.pg_haplotype_sample(device, C.byref(ps), size, recombrate, effective_N, int(add_reference), allele_penalty,
+                                        ptr(paths), ptr(scores), ptr(p2a), ptr(nk), ptr(counts)))
+    return paths, scores, p2a, nk, counts[:int(nk.sum())]
+
+
 class HMM:
     """HMM(unique_kmers, probabilities, run_genotyping, run_phasing, recombrate, uniform, effective_N,
     only_paths, normalize) (src/hmm.hpp:38).  Viterbi phasing is out of scope."""

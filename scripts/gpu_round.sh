@@ -33,6 +33,19 @@ ncu_probe)
 ncu_scatter)
   PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"count_tile_kernel" -s 30 -c 2 -o $out/prof_scatter_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3} > $out/ncu_scatter_$tag.out 2>&1; tail -3 $out/ncu_scatter_$tag.out;;
+ncu_skel)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"skeleton" -c 2 -o $out/prof_skel_$tag \
+     python scripts/bench_hmm.py --haplotypes ${H:-64} --variants 100000 --repeat 1 > $out/ncu_skel_$tag.out 2>&1; tail -3 $out/ncu_skel_$tag.out;;
+sweep_slices)
+  for kb in 16384 24576 32768 49152 65536 98304; do
+    PG_COUNT_PART_KB=$kb PG_BENCH_E2E_STEPS=0 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > $out/bench_slice${kb}_$tag.json 2> $out/bench_slice${kb}_$tag.err
+    python - <<EOF
+import json
+d=json.loads([l for l in open("$out/bench_slice${kb}_$tag.json") if l.startswith("{")][0])
+u=d["roofline"]["update_pass"]
+print("slice_kb", $kb, "step_ms", round(d["ms_per_step"],1), "update_ms", round(u["ms"],1), "probe_ms", round(u["probe_ms"],1), "passes", u["probe_passes"])
+EOF
+  done;;
 hmm_lean)
   for lean in 0 1; do
     PG_SKELETON_LEAN=$lean timeout 900 python scripts/bench_hmm.py --haplotypes 32 64 --variants 400000 --repeat 2 > $out/bench_hmm_lean${lean}_$tag.jsonl 2> $out/bench_hmm_lean${lean}_$tag.err
