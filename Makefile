@@ -16,9 +16,14 @@ $(LIB): $(SRCS) $(HDRS)
 	@grep -E "error|warning: v|spill" build_ptxas.log | grep -v "0 bytes spill" | head -40 || true
 
 # C++ host of the `-f` stage over the C-ABI only (no jellyfish, no cereal)
-tools: integration/genotype_from_index
+tools: integration/genotype_from_index integration/genotype_sharded
 integration/genotype_from_index: integration/genotype_from_index.cpp include/pangenie_b200.h $(LIB)
 	g++ -std=c++17 -O2 -Wall -Iinclude $< -Lpangenie_b200 -lpangenie_b200 -Wl,-rpath,'$$ORIGIN/../pangenie_b200' -o $@
+
+# the same stage for one sample sharded over the GPUs of a box: C-ABI + NCCL (one all-reduce), one host thread per GPU
+integration/genotype_sharded: integration/genotype_sharded.cpp include/pangenie_b200.h $(LIB)
+	g++ -std=c++17 -O2 -Wall -Iinclude -I/usr/local/cuda/include $< -Lpangenie_b200 -lpangenie_b200 -L/usr/local/cuda/lib64 -lcudart -lnccl -pthread \
+	  -Wl,-rpath,'$$ORIGIN/../pangenie_b200' -Wl,-rpath,/usr/local/cuda/lib64 -o $@
 
 oracle:
 	$(MAKE) -C oracle oracle
@@ -26,5 +31,5 @@ ref:
 	$(MAKE) -C oracle ref
 
 clean:
-	rm -f $(LIB) build_ptxas.log integration/genotype_from_index
+	rm -f $(LIB) build_ptxas.log integration/genotype_from_index integration/genotype_sharded
 	$(MAKE) -C oracle clean

@@ -575,33 +575,46 @@ struct LeanChain : Chain<L, CPL, 1, NT> {
     return t0 + t1;  // the same expression in every thread: bitwise identical
   }
 
-  // one biallelic column with T = total of the previous state > 0; reads rs[cbuf], writes rs[nbuf] and wt[nbuf]
-  template <bool BACKWARD>
-  __device__ __forceinline__ void step_lean(int slot, int cbuf, int nbuf, double T, int ebuf) {
+  // Shared-memory inputs of a biallelic column that do not depend on the total: row sums and emissions of my columns.
+  // Issued as one batch right after the barrier, so their latency overlaps the reduction of the total (measured: with the
+  // loads left next to their uses a quarter of all stall samples sat on the short scoreboard).
+  __device__ __forceinline__ void load_inputs(int slot, int cbuf, int ebuf, double (&rjv)[CPL], double (&ejv)[CPL]) const {
     const double* d = this->desc_d(slot);
-    constexpr int o = BACKWARD ? 4 : 0;
-    const double sc = pow2_scale_of(T);
-    const double ca = d[o] * sc, cb = d[o + 1] * sc, cc = d[o + 2] * T * sc;
     const int i = this->row(0);
     const bool rok = i < this->P;
     const unsigned long long* bw = reinterpret_cast<const unsigned long long*>(d + DESC_BITS_AT);
     const int ib = rok ? (int)((bw[i >> 6] >> (i & 63)) & 1ull) : 2;
     const double* ej = &ls->ecol[ebuf][ib][this->col0];
     const double* rj = &this->sm->rs[cbuf][this->col0];
-    const double rho = fma(cb, this->rrow[0], cc);
-    double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
-      const double u = fma(cb, rj[s], rho);
-      const double v = fma(ca, this->x[0][s], u) * ej[s];
-      this->x[0][s] = v;
-      if (s & 1) acc1 += v;
-      else acc0 += v;
+      rjv[s] = rj[s];
+      ejv[s] = ej[s];
     }
-    double acc = this->row_reduce(acc0 + acc1);
-    this->rrow[0] = acc;
-    if (this->lc == 0 && rok) this->sm->rs[nbuf][i] = acc;
-    double wsum = acc;  // every lane of a row group holds the row sum: add over the row groups of the warp
+  }
+
+  // one biallelic column with T = total of the previous state > 0; writes rs[nbuf] and wt[nbuf]
+  template <bool BACKWARD>
+  __device__ __forceinline__ void step_lean(int slot, int nbuf, double T, const double (&rjv)[CPL], const double (&ejv)[CPL]) {
+    const double* d = this->desc_d(slot);
+    constexpr int o = BACKWARD ? 4 : 0;
+    const double sc = pow2_scale_of(T);
+    const double ca = d[o] * sc, cb = d[o + 1] * sc, cc = d[o + 2] * T * sc;
+    const int i = this->row(0);
+    const bool rok = i < this->P;
+    const double rho = fma(cb, this->rrow[0], cc);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four partial sums: the dependent DADD chain is CPL/4 long
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) {
+      const double u = fma(cb, rjv[s], rho);
+      const double v = fma(ca, this->x[0][s], u) * ejv[s];
+      this->x[0][s] = v;
+      acc[s & 3] += v;
+    }
+    double a = this->row_reduce((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    this->rrow[0] = a;
+    if (this->lc == 0 && rok) this->sm->rs[nbuf][i] = a;
+    double wsum = a;  // every lane of a row group holds the row sum: add over the row groups of the warp
 #pragma unroll
     for (int q = L; q < 32; q <<= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, q);
     if (this->lane == 0) ls->wt[nbuf][this->w] = wsum;
@@ -609,7 +622,7 @@ struct LeanChain : Chain<L, CPL, 1, NT> {
 };
 
 template <int L, int CPL, int NT>
-__global__ void __launch_bounds__(NT) skeleton_lean_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(NT, 1) skeleton_lean_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LeanSmem* ls = reinterpret_cast<LeanSmem*>(smem_raw);
   ChainSmem* sm = &ls->base;
@@ -625,6 +638,7 @@ __global__ void __launch_bounds__(NT) skeleton_lean_kernel(const ChainParams p) 
   const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
   const size_t CS = p.ckpt_stride;
   double nou[1][CPL];
+  double rjv[CPL], ejv[CPL];
   constexpr int D = HMM_PREFETCH;
   static_assert(D >= 2, "the emission table of column t+1 is built while column t is processed");
   int cur = 0;
@@ -655,9 +669,11 @@ __global__ void __launch_bounds__(NT) skeleton_lean_kernel(const ChainParams p) 
         until_ckpt = B;
       }
       --until_ckpt;
+      const bool bial = header_A(slot) <= 2;
+      if (bial) ch.load_inputs(slot, cur, t & 1, rjv, ejv);
       const double T = have_wt ? ch.total_from_warps(cur) : ch.total(cur);
-      if (header_A(slot) <= 2 && T > 0.0) {
-        ch.template step_lean<false>(slot, cur, cur ^ 1, T, t & 1);
+      if (bial && T > 0.0) {
+        ch.template step_lean<false>(slot, cur ^ 1, T, rjv, ejv);
         have_wt = true;
       } else {
         ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nou, 0);
@@ -697,9 +713,11 @@ __global__ void __launch_bounds__(NT) skeleton_lean_kernel(const ChainParams p) 
         --blk;
       }
       --rel;
+      const bool bial = header_A(slot) <= 2;
+      if (bial) ch.load_inputs(slot, cur, t & 1, rjv, ejv);
       const double T = have_wt ? ch.total_from_warps(cur) : ch.total(cur);
-      if (header_A(slot) <= 2 && T > 0.0) {
-        ch.template step_lean<true>(slot, cur, cur ^ 1, T, t & 1);
+      if (bial && T > 0.0) {
+        ch.template step_lean<true>(slot, cur ^ 1, T, rjv, ejv);
         have_wt = true;
       } else {
         ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nou, 0);

@@ -524,6 +524,7 @@ struct PartArgs {
   uint32_t* item_start;   // [n_parts * PART_REPL + 1] first probe item of every region (part_items_kernel)
   uint32_t region_cap;
   uint32_t n_parts;
+  uint32_t item;          // k-mers per probe work item
 };
 __device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
   return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
@@ -806,7 +807,10 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
 
 // Works through the partition buffers in partition order (persistent CTAs pulling items of PP_ITEM k-mers), so the
 // CTAs running at any moment hit one or two adjacent slices of the table.
-constexpr int PP_ITEM = 8192;
+// k-mers per work item of the probe pass.  The CTAs running at any moment work on neighbouring items, i.e. on
+// gridDim * item consecutive k-mers of the partition-ordered stream; the table slices those k-mers fall into are the working
+// set that has to stay in the L2 (PG_COUNT_PROBE_ITEM: tuning knob).
+constexpr int PP_ITEM = 1024;
 constexpr bool PP_QUEUE = false;  // park overflow walks in a shared-memory queue (barriers per item) or walk in place
 constexpr int PP_BATCH = 4;  // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
 // item_start[r] = first probe item of region r (exclusive scan of ceil(fill / PP_ITEM) over the regions); one CTA
@@ -816,7 +820,7 @@ __global__ void __launch_bounds__(1024) part_items_kernel(const PartArgs pa) {
   const uint32_t per = (n_regions + 1023) / 1024;
   const uint32_t r0 = threadIdx.x * per, r1 = min(r0 + per, n_regions);
   uint32_t sum = 0;
-  for (uint32_t r = r0; r < r1; ++r) sum += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + PP_ITEM - 1) / PP_ITEM;
+  for (uint32_t r = r0; r < r1; ++r) sum += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + pa.item - 1) / pa.item;
   s_sum[threadIdx.x] = sum;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {
@@ -828,7 +832,7 @@ __global__ void __launch_bounds__(1024) part_items_kernel(const PartArgs pa) {
   uint32_t run = threadIdx.x ? s_sum[threadIdx.x - 1] : 0u;
   for (uint32_t r = r0; r < r1; ++r) {
     pa.item_start[r] = run;
-    run += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + PP_ITEM - 1) / PP_ITEM;
+    run += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + pa.item - 1) / pa.item;
   }
   if (threadIdx.x == 1023) pa.item_start[n_regions] = s_sum[1023];
 }
@@ -853,9 +857,9 @@ __global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2
     }
     const uint32_t q = lo;
     const uint32_t nq = min(pa.cursor[(size_t)q * CURSOR_STRIDE], pa.region_cap);
-    const uint32_t off = (item - s_start[q]) * PP_ITEM;
+    const uint32_t off = (item - s_start[q]) * pa.item;
     const uint64_t* src = pa.buf + (size_t)q * pa.region_cap + off;
-    const uint32_t m = min((uint32_t)PP_ITEM, nq - off);
+    const uint32_t m = min(pa.item, nq - off);
     // the k-mer stream comes from HBM: the next round's k-mers are requested before the current round is probed
     uint64_t nx[PP_BATCH];
 #pragma unroll
@@ -1130,6 +1134,7 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is
   pa.item_start = c->d_part_cursor + PART_CURSOR_WORDS;
   pa.region_cap = (uint32_t)region;
   pa.n_parts = n_parts;
+  pa.item = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(env_u64("PG_COUNT_PROBE_ITEM", PP_ITEM), 256), 1u << 20);
   // text per pass the regions are sized for (the excess of an over-full region is probed directly, so an underestimate
   // of the k-mer density costs speed, not correctness)
   super = std::max<uint64_t>((uint64_t)((double)(region * n_regions) / (density * slack)), 1ull << 20);

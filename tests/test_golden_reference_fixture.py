@@ -99,3 +99,23 @@ def test_cpp_host_runs_the_stage_from_the_index_files(engine):
         lik = np.array([float(x) for x in row[6].split(",")])
         want = res[0].likelihoods[int(res[0].gl_offsets[v]):int(res[0].gl_offsets[v + 1])]
         np.testing.assert_allclose(lik, want, rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cpp_sharded_host_matches_the_single_gpu_host():
+    """integration/genotype_sharded.cpp (C-ABI + NCCL: canonical PRIME on every GPU, read ranges, one all-reduce of the count
+    array) prints exactly what the single-GPU host prints; with two visible GPUs the sample is really sharded."""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    one, many = os.path.join(root, "integration", "genotype_from_index"), os.path.join(root, "integration", "genotype_sharded")
+    if not (os.path.exists(one) and os.path.exists(many)):
+        pytest.skip("integration tools not built (make tools)")
+    args = [os.path.join(G, "index"), os.path.join(G, "region-reads.fa")]
+    want = subprocess.run([one] + args, capture_output=True, text=True)
+    assert want.returncode == 0, want.stderr
+    for n in sorted({1, min(2, torch.cuda.device_count())}):
+        got = subprocess.run([many] + args + [str(n)], capture_output=True, text=True, timeout=600)
+        assert got.returncode == 0, got.stderr[-2000:]
+        assert got.stdout == want.stdout, n
+        assert got.stderr.strip().splitlines()[-1] == want.stderr.strip().splitlines()[-1]   # the k-mer abundance peak

@@ -19,7 +19,7 @@ def test_sampler_matches_reference_class(oracle, seed):
     n_paths = int([2, 3, 8, 20, 33, 64, 65, 129][seed])
     panel = random_panel(rng, int(rng.integers(2, 300)), n_paths, max_alleles=int(rng.choice([2, 2, 4])),
                          undefined_frac=0.1 if seed % 2 else 0.0, shared_kmer_frac=0.3, ref_only_frac=0.1,
-                         kmers_per_allele=(0, 8), count_range=(0, 12), spacing=(50, 200000))
+                         kmers_per_allele=(0, 6), count_range=(0, 12), spacing=(50, 200000))   # (the reference's KmerPath16 holds 16 k-mers)
     for size, add_ref, penalty, eff_n in ((1, False, 10, 25000.0), (min(n_paths, 5), True, 5, 0.01), (min(n_paths, 15), False, 10, 1e-5)):
         want = oracles.cpu_haplotype_sample(lib, prefix, panel, size, effective_N=eff_n, add_reference=add_ref, allele_penalty=penalty)
         got = pg.haplotype_sample(panel, size, effective_N=eff_n, add_reference=add_ref, allele_penalty=penalty)
