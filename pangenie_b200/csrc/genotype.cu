@@ -479,18 +479,7 @@ static cudaError_t launch_block(const ChainParams& p, int grid_blocks, cudaStrea
 template <int L, int CPL, int RPW, int NT>
 static cudaError_t launch_pair(const ChainParams& p, uint32_t n_chrom, int grid_blocks, cudaStream_t s, bool skeleton, bool blocks) {
   const size_t smem = sizeof(ChainSmem);
-  if (skeleton) {
-    // one row per thread and more than one warp (16 < P <= 68): the lean walk (hmm_kernels.cuh); PG_SKELETON_LEAN=0 keeps
-    // the generic one (test / comparison knob)
-    const char* lean_env = getenv("PG_SKELETON_LEAN");
-    const bool lean_on = !(lean_env && lean_env[0] == '0');
-    if constexpr (RPW == 1 && NT > 32) {
-      if (lean_on) skeleton_lean_kernel<L, CPL, NT><<<dim3(n_chrom, 2), NT, sizeof(LeanSmem), s>>>(p);
-      else skeleton_kernel<L, CPL, RPW, NT><<<dim3(n_chrom, 2), NT, smem, s>>>(p);
-    } else {
-      skeleton_kernel<L, CPL, RPW, NT><<<dim3(n_chrom, 2), NT, smem, s>>>(p);
-    }
-  }
+  if (skeleton) skeleton_kernel<L, CPL, RPW, NT><<<dim3(n_chrom, 2), NT, smem, s>>>(p);
   if (blocks) {
     if (NT > 288) return launch_block<L, CPL, RPW, NT, 1>(p, grid_blocks, s);
     switch (block_minb(NT)) {

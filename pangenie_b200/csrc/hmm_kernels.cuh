@@ -524,219 +524,6 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// phase 1, lean form for 16 < P <= 68 (one row per thread): the walk above is not HBM-bound but ISSUE- and
-// latency-bound (ncu at P = 65: 608 instructions per warp and column for 17 cells, 2300 cycles per column, the fp64
-// pipe of one SM allows ~400).  Biallelic columns with a live previous total take this path:
-//   * the emission of every (row class, column) pair of the NEXT column is tabulated once per column by the CTA
-//     (2 x L*CPL doubles in shared memory, zero beyond P), so a cell is 2 DFMA + 1 DMUL + 1 DADD + 2 LDS - no selects,
-//     no per-cell masks;
-//   * the total comes from per-warp partial sums published together with the row sums (NW values to add after the
-//     barrier) instead of a second 5-level shuffle reduction over all row sums.
-// Multi-allelic columns, first columns and columns after an underflow fall back to Chain::step().
-// -------------------------------------------------------------------------------------------------
-struct LeanSmem {
-  ChainSmem base;
-  double ecol[2][3][HMM_RS_PAD];  // [column parity][row class 0 / 1 / invalid row][column]: emission, 0 beyond P
-  double wt[2][32];               // per-warp partial totals of the state whose row sums sit in rs[buf]
-};
-
-template <int L, int CPL, int NT>
-struct LeanChain : Chain<L, CPL, 1, NT> {
-  using Base = Chain<L, CPL, 1, NT>;
-  static constexpr int NW = NT / 32;
-  LeanSmem* ls;
-
-  // emission table of the column whose descriptor sits in ring slot `slot` (all threads; A <= 2 only)
-  __device__ __forceinline__ void build_ecol(int slot, int ebuf) const {
-    const double* d = this->desc_d(slot);
-    const uint32_t A = reinterpret_cast<const uint32_t*>(d + 8)[0];
-    if (A > 2) return;
-    const unsigned long long* bw = reinterpret_cast<const unsigned long long*>(d + DESC_BITS_AT);
-    constexpr int NC = L * CPL;
-    for (int idx = threadIdx.x; idx < 2 * NC; idx += NT) {
-      const int ib = idx >= NC ? 1 : 0, j = idx - ib * NC;
-      double e = 0.0;
-      if (j < this->P) {
-        const uint32_t jb = (uint32_t)((bw[j >> 6] >> (j & 63)) & 1ull);
-        e = d[10 + ib * HMM_FAST_A + jb];
-      }
-      ls->ecol[ebuf][ib][j] = e;
-    }
-  }
-
-  __device__ __forceinline__ double total_from_warps(int buf) const {
-    double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-    for (int q = 0; q + 1 < NW; q += 2) {
-      t0 += ls->wt[buf][q];
-      t1 += ls->wt[buf][q + 1];
-    }
-    if (NW & 1) t0 += ls->wt[buf][NW - 1];
-    return t0 + t1;  // the same expression in every thread: bitwise identical
-  }
-
-  // Shared-memory inputs of a biallelic column that do not depend on the total: row sums and emissions of my columns.
-  // Issued as one batch right after the barrier, so their latency overlaps the reduction of the total (measured: with the
-  // loads left next to their uses a quarter of all stall samples sat on the short scoreboard).
-  __device__ __forceinline__ void load_inputs(int slot, int cbuf, int ebuf, double (&rjv)[CPL], double (&ejv)[CPL]) const {
-    const double* d = this->desc_d(slot);
-    const int i = this->row(0);
-    const bool rok = i < this->P;
-    const unsigned long long* bw = reinterpret_cast<const unsigned long long*>(d + DESC_BITS_AT);
-    const int ib = rok ? (int)((bw[i >> 6] >> (i & 63)) & 1ull) : 2;
-    const double* ej = &ls->ecol[ebuf][ib][this->col0];
-    const double* rj = &this->sm->rs[cbuf][this->col0];
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-      rjv[s] = rj[s];
-      ejv[s] = ej[s];
-    }
-  }
-
-  // one biallelic column with T = total of the previous state > 0; writes rs[nbuf] and wt[nbuf]
-  template <bool BACKWARD>
-  __device__ __forceinline__ void step_lean(int slot, int nbuf, double T, const double (&rjv)[CPL], const double (&ejv)[CPL]) {
-    const double* d = this->desc_d(slot);
-    constexpr int o = BACKWARD ? 4 : 0;
-    const double sc = pow2_scale_of(T);
-    const double ca = d[o] * sc, cb = d[o + 1] * sc, cc = d[o + 2] * T * sc;
-    const int i = this->row(0);
-    const bool rok = i < this->P;
-    const double rho = fma(cb, this->rrow[0], cc);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four partial sums: the dependent DADD chain is CPL/4 long
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-      const double u = fma(cb, rjv[s], rho);
-      const double v = fma(ca, this->x[0][s], u) * ejv[s];
-      this->x[0][s] = v;
-      acc[s & 3] += v;
-    }
-    double a = this->row_reduce((acc[0] + acc[1]) + (acc[2] + acc[3]));
-    this->rrow[0] = a;
-    if (this->lc == 0 && rok) this->sm->rs[nbuf][i] = a;
-    double wsum = a;  // every lane of a row group holds the row sum: add over the row groups of the warp
-#pragma unroll
-    for (int q = L; q < 32; q <<= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, q);
-    if (this->lane == 0) ls->wt[nbuf][this->w] = wsum;
-  }
-};
-
-template <int L, int CPL, int NT>
-__global__ void __launch_bounds__(NT, 1) skeleton_lean_kernel(const ChainParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  LeanSmem* ls = reinterpret_cast<LeanSmem*>(smem_raw);
-  ChainSmem* sm = &ls->base;
-  LeanChain<L, CPL, NT> ch;
-  ch.init(sm, &p);
-  ch.ls = ls;
-  const ChromCols cc = p.chroms[blockIdx.x];
-  if (cc.n_blocks <= 1) return;
-  if (p.seq_flags && !p.seq_flags[blockIdx.x]) return;
-  for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;      // zero padding beyond P
-  for (int i = threadIdx.x; i < 2 * 3 * HMM_RS_PAD; i += NT) (&ls->ecol[0][0][0])[i] = 0.0;  // incl. the all-zero class of invalid rows
-  ch.sync();
-  const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
-  const size_t CS = p.ckpt_stride;
-  double nou[1][CPL];
-  double rjv[CPL], ejv[CPL];
-  constexpr int D = HMM_PREFETCH;
-  static_assert(D >= 2, "the emission table of column t+1 is built while column t is processed");
-  int cur = 0;
-  bool have_wt = false;
-  auto header_A = [&](int slot) { return reinterpret_cast<const uint32_t*>(ch.desc_d(slot) + 8)[0]; };
-  if (blockIdx.y == 0) {
-    const int last = c0 + (int)(cc.n_blocks - 1) * B - 1;
-    int slot = ch.slot_of(c0), pslot = slot;
-    for (int d = 0; d < D; ++d) {
-      ch.prefetch_desc(c0 + d, c0, c1, pslot);
-      pslot = ch.slot_next(pslot);
-    }
-    cp_async_wait<D - 2>();  // descriptors of c0 and c0 + 1 have landed
-    ch.sync();
-    ch.template step<false, true, false>(slot, 0, 0, 0.0, nou, 0);
-    if (c0 + 1 <= last) ch.build_ecol(ch.slot_next(slot), (c0 + 1) & 1);
-    ch.prefetch_desc(c0 + D, c0, c1, pslot);
-    pslot = ch.slot_next(pslot);
-    cp_async_wait<D - 2>();
-    ch.sync();
-    slot = ch.slot_next(slot);
-    int until_ckpt = B - 1;
-    uint32_t blk = cc.blk_begin + 1;
-    for (int t = c0 + 1; t <= last; ++t) {
-      if (until_ckpt == 0) {
-        ch.store_dense(p.ckpt_fwd + (size_t)blk * CS);
-        ++blk;
-        until_ckpt = B;
-      }
-      --until_ckpt;
-      const bool bial = header_A(slot) <= 2;
-      if (bial) ch.load_inputs(slot, cur, t & 1, rjv, ejv);
-      const double T = have_wt ? ch.total_from_warps(cur) : ch.total(cur);
-      if (bial && T > 0.0) {
-        ch.template step_lean<false>(slot, cur ^ 1, T, rjv, ejv);
-        have_wt = true;
-      } else {
-        ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nou, 0);
-        have_wt = false;
-      }
-      if (t + 1 <= last) ch.build_ecol(ch.slot_next(slot), (t + 1) & 1);
-      ch.prefetch_desc(t + D, c0, c1, pslot);
-      pslot = ch.slot_next(pslot);
-      cp_async_wait<D - 2>();
-      ch.sync();
-      slot = ch.slot_next(slot);
-      cur ^= 1;
-    }
-    ch.store_dense(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * CS);
-  } else {
-    const int first = c0 + B;
-    int slot = ch.slot_of(c1 - 1), pslot = slot;
-    for (int d = 0; d < D; ++d) {
-      ch.prefetch_desc(c1 - 1 - d, c0, c1, pslot);
-      pslot = ch.slot_prev(pslot);
-    }
-    cp_async_wait<D - 2>();
-    ch.sync();
-    ch.template step<true, true, false>(slot, 0, 0, 0.0, nou, 0);
-    int rel = (c1 - 1 - c0) % B;
-    uint32_t blk = cc.blk_begin + (uint32_t)((c1 - 1 - c0) / B);
-    if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
-    if (c1 - 2 >= first) ch.build_ecol(ch.slot_prev(slot), (c1 - 2) & 1);
-    ch.prefetch_desc(c1 - 1 - D, c0, c1, pslot);
-    pslot = ch.slot_prev(pslot);
-    cp_async_wait<D - 2>();
-    ch.sync();
-    slot = ch.slot_prev(slot);
-    for (int t = c1 - 2; t >= first; --t) {
-      if (rel == 0) {
-        rel = B;
-        --blk;
-      }
-      --rel;
-      const bool bial = header_A(slot) <= 2;
-      if (bial) ch.load_inputs(slot, cur, t & 1, rjv, ejv);
-      const double T = have_wt ? ch.total_from_warps(cur) : ch.total(cur);
-      if (bial && T > 0.0) {
-        ch.template step_lean<true>(slot, cur ^ 1, T, rjv, ejv);
-        have_wt = true;
-      } else {
-        ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nou, 0);
-        have_wt = false;
-      }
-      if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
-      if (t - 1 >= first) ch.build_ecol(ch.slot_prev(slot), (t - 1) & 1);
-      ch.prefetch_desc(t - D, c0, c1, pslot);
-      pslot = ch.slot_prev(pslot);
-      cp_async_wait<D - 2>();
-      ch.sync();
-      slot = ch.slot_prev(slot);
-      cur ^= 1;
-    }
-  }
-  cp_async_wait<0>();
-}
-
-// -------------------------------------------------------------------------------------------------
 // phase 2: block forward-backward with fused posterior.  Persistent CTAs pull (chromosome, block) jobs.
 // -------------------------------------------------------------------------------------------------
 template <int L, int CPL, int RPW, int NT, int MINB>

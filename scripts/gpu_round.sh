@@ -57,6 +57,15 @@ u=d["roofline"]["update_pass"]
 print("slice_kb", $1, "item", $2, "step_ms", round(d["ms_per_step"],1), "update_ms", round(u["ms"],1), "probe_ms", round(u["probe_ms"],1), "scatter_ms", round(u["ms"]-u["probe_ms"],1), "passes", u["probe_passes"])
 EOF
   done;;
+direct)
+  PG_COUNT_PART_KB=0 PG_BENCH_E2E_STEPS=0 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > $out/bench_direct_$tag.json 2> $out/bench_direct_$tag.err
+  python - <<EOF
+import json
+d=json.loads([l for l in open("$out/bench_direct_$tag.json") if l.startswith("{")][0])
+u=d["roofline"]["update_pass"]
+print("direct (no partitioning): step_ms", round(d["ms_per_step"],1), "update_ms", round(u["ms"],1))
+EOF
+  ;;
 hmm_lean)
   for lean in 0 1; do
     PG_SKELETON_LEAN=$lean timeout 900 python scripts/bench_hmm.py --haplotypes 32 64 --variants 400000 --repeat 2 > $out/bench_hmm_lean${lean}_$tag.jsonl 2> $out/bench_hmm_lean${lean}_$tag.err

@@ -258,37 +258,3 @@ def test_path_counts_at_kernel_configuration_boundaries(engine, oracle, n_paths)
         want = oracles.cpu_hmm_run(oracle, "pgo_", [panel], table, **kw)[0]
         got = engine.hmm_run([panel], table, **kw)[0]
         assert_results_close(got, want, atol=1e-300, label=f"P={n_paths} normalize={normalize}")
-
-
-@pytest.mark.parametrize("n_paths", [20, 33, 65])
-def test_lean_and_generic_skeleton_agree(engine, oracle, monkeypatch, n_paths):
-    """The lean checkpoint walk (biallelic columns: tabulated emissions, per-warp partial totals) against the generic one
-    on chains of many blocks, with multi-allelic columns and columns whose total underflows in between, and both against
-    the oracle."""
-    rng = np.random.default_rng(700 + n_paths)
-    panel = random_panel(rng, 1200, n_paths, max_alleles=3, undefined_frac=0.05, ref_only_frac=0.02, kmers_per_allele=(0, 8))
-    table = _table()
-    # emission tables with exact zeros: some column totals are exactly zero (the reference's uniform replacement)
-    probs = pg.ProbabilityTable(0, 1, 21, 0.0)
-    probs.modify_probability(0, 10, 0.0, 1.0, 0.0)
-    probs.modify_probability(0, 20, 0.0, 0.0, 1.0)
-    probs.modify_probability(0, 0, 1.0, 0.0, 0.0)
-    b = pg.PanelBuilder()
-    pos = 1000
-    for i in range(500):
-        pos += int(rng.integers(100, 2000))
-        al = rng.integers(0, 2, size=n_paths)
-        al[0], al[1] = 0, 1
-        v = b.add_variant(pos, al)
-        c = [(10, 10), (20, 0), (0, 20), (10, 0)][int(rng.integers(0, 4))]
-        b.insert_kmer(v, c[0], [0]); b.insert_kmer(v, c[1], [1])
-    dead = b.build()
-    for p, t, kw in ((panel, table, dict(recombrate=1.26, effective_N=1e-5)), (dead, probs, dict(recombrate=1.26, effective_N=25000.0))):
-        monkeypatch.setenv("PG_SKELETON_LEAN", "0")
-        generic = engine.hmm_run([p], t, **kw)[0]
-        monkeypatch.setenv("PG_SKELETON_LEAN", "1")
-        lean = engine.hmm_run([p], t, **kw)[0]
-        assert np.array_equal(lean.is_column, generic.is_column) and np.array_equal(lean.genotype, generic.genotype)
-        np.testing.assert_allclose(lean.likelihoods, generic.likelihoods, rtol=1e-10, atol=1e-300)
-        want = oracles.cpu_hmm_run(oracle, "pgo_", [p], t, **kw)[0]
-        assert_results_close(lean, want, atol=1e-300, label=f"lean skeleton P={n_paths}")
