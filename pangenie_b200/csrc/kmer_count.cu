@@ -521,10 +521,9 @@ constexpr int CURSOR_STRIDE = 32;
 struct PartArgs {
   uint64_t* buf;          // [n_parts * PART_REPL][region_cap] canonical k-mers
   uint32_t* cursor;       // [n_parts * PART_REPL * CURSOR_STRIDE] k-mers appended (may run past region_cap: the excess was probed directly)
-  uint32_t* item_start;   // [n_parts * PART_REPL + 1] first probe item of every region (part_items_kernel)
+  uint32_t* work;         // [n_parts] chunks of every partition handed out so far (probe pass)
   uint32_t region_cap;
   uint32_t n_parts;
-  uint32_t item;          // k-mers per probe work item
 };
 __device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
   return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
@@ -805,83 +804,70 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   }
 }
 
-// Works through the partition buffers in partition order (persistent CTAs pulling items of PP_ITEM k-mers), so the
-// CTAs running at any moment hit one or two adjacent slices of the table.
-// k-mers per work item of the probe pass.  The CTAs running at any moment work on neighbouring items, i.e. on
-// gridDim * item consecutive k-mers of the partition-ordered stream; the table slices those k-mers fall into are the working
-// set that has to stay in the L2 (PG_COUNT_PROBE_ITEM: tuning knob).
-constexpr int PP_ITEM = 1024;
+// Probe pass over the filled partition buffers.  ALL CTAs of the (co-resident) grid march through the partitions together:
+// within a partition the k-mers of its PART_REPL regions are handed out in chunks of PP_CHUNK from a per-partition work
+// counter, and a CTA moves on to the next partition only when the current one has nothing left to hand out - so at any
+// moment the whole GPU probes one or two neighbouring table slices, and the working set that has to stay in the L2 is the
+// slice size, whatever the number of k-mers per pass.  (Dealing work items statically - round-robin over the grid - lets
+// the persistent CTAs drift apart over the thousands of items of a pass until they span hundreds of MB of table; measured
+// at configs[2] with 16 MB slices: 234 GB of DRAM reads per pass of 1.8 G k-mers, L2 hit rate 22%, i.e. every probe a burst.)
+constexpr int PP_CHUNK = 1024;
 constexpr bool PP_QUEUE = false;  // park overflow walks in a shared-memory queue (barriers per item) or walk in place
 constexpr int PP_BATCH = 4;  // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
-// item_start[r] = first probe item of region r (exclusive scan of ceil(fill / PP_ITEM) over the regions); one CTA
-__global__ void __launch_bounds__(1024) part_items_kernel(const PartArgs pa) {
-  __shared__ uint32_t s_sum[1024];
-  const uint32_t n_regions = pa.n_parts * PART_REPL;
-  const uint32_t per = (n_regions + 1023) / 1024;
-  const uint32_t r0 = threadIdx.x * per, r1 = min(r0 + per, n_regions);
-  uint32_t sum = 0;
-  for (uint32_t r = r0; r < r1; ++r) sum += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + pa.item - 1) / pa.item;
-  s_sum[threadIdx.x] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const uint32_t a = (int)threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0u;
-    __syncthreads();
-    s_sum[threadIdx.x] += a;
-    __syncthreads();
-  }
-  uint32_t run = threadIdx.x ? s_sum[threadIdx.x - 1] : 0u;
-  for (uint32_t r = r0; r < r1; ++r) {
-    pa.item_start[r] = run;
-    run += (min(pa.cursor[(size_t)r * CURSOR_STRIDE], pa.region_cap) + pa.item - 1) / pa.item;
-  }
-  if (threadIdx.x == 1023) pa.item_start[n_regions] = s_sum[1023];
-}
+static_assert(PP_CHUNK == PP_BATCH * 256, "one chunk = one round of the CTA");
 
 template <int OP>
 __global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, const TableRef T) {
   __shared__ WalkQueue s_wq;
+  __shared__ uint32_t s_fill[2][PART_REPL];  // k-mers in the regions of the current partition (double-buffered)
+  __shared__ uint32_t s_chunk[2];             // chunk being probed / the next one, already requested
   const int tid = threadIdx.x;
   if (tid == 0) s_wq.n = 0;
-  __syncthreads();
-  const uint32_t n_regions = pa.n_parts * PART_REPL;
-  const uint32_t* __restrict__ s_start = pa.item_start;  // regions in partition order (part_items_kernel)
-  const uint32_t total = s_start[n_regions];
   uint32_t inserted = 0;
-  // items are dealt round-robin: the CTAs running at any moment work on neighbouring items = the same table slice
-  for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
-    uint32_t lo = 0, hi = n_regions;  // largest q with s_start[q] <= item (regions without items share their successor's start)
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s_start[mid] <= item) lo = mid;
-      else hi = mid;
-    }
-    const uint32_t q = lo;
-    const uint32_t nq = min(pa.cursor[(size_t)q * CURSOR_STRIDE], pa.region_cap);
-    const uint32_t off = (item - s_start[q]) * pa.item;
-    const uint64_t* src = pa.buf + (size_t)q * pa.region_cap + off;
-    const uint32_t m = min(pa.item, nq - off);
-    // the k-mer stream comes from HBM: the next round's k-mers are requested before the current round is probed
-    uint64_t nx[PP_BATCH];
+  if (tid < PART_REPL) s_fill[0][tid] = min(pa.cursor[(size_t)tid * CURSOR_STRIDE], pa.region_cap);
+  __syncthreads();
+  for (uint32_t q = 0; q < pa.n_parts; ++q) {
+    const int cur = (int)(q & 1u);
+    // fills of the next partition on their way while this one is probed
+    if (tid < PART_REPL && q + 1 < pa.n_parts)
+      s_fill[cur ^ 1][tid] = min(pa.cursor[(size_t)((q + 1) * PART_REPL + tid) * CURSOR_STRIDE], pa.region_cap);
+    // chunk c of the partition = chunk (c - first[r]) of region r
+    uint32_t first[PART_REPL + 1];
+    first[0] = 0;
 #pragma unroll
-    for (int i = 0; i < PP_BATCH; ++i) {
-      const uint32_t j = (uint32_t)i * 256 + (uint32_t)tid;
-      nx[i] = j < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
-    }
-#pragma unroll 1
-    for (uint32_t r = 0; r < m; r += PP_BATCH * 256) {
+    for (int r = 0; r < PART_REPL; ++r) first[r + 1] = first[r] + (s_fill[cur][r] + PP_CHUNK - 1) / PP_CHUNK;
+    const uint32_t total = first[PART_REPL];
+    if (tid == 0) s_chunk[0] = total ? atomicAdd(pa.work + q, 1u) : 0u;
+    __syncthreads();
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t c = s_chunk[k & 1u];
+      if (c >= total) break;
+      if (tid == 0) s_chunk[(k + 1u) & 1u] = atomicAdd(pa.work + q, 1u);   // in flight while this chunk is probed
+      int r = 0;
+#pragma unroll
+      for (int u = 1; u < PART_REPL; ++u) r += c >= first[u] ? 1 : 0;   // regions without chunks share their successor's start
+      uint32_t fr = 0, nr = 0;
+#pragma unroll
+      for (int u = 0; u < PART_REPL; ++u) {   // (register array indexed by a loop-carried value: select instead of local memory)
+        fr = u == r ? first[u] : fr;
+        nr = u == r ? s_fill[cur][u] : nr;
+      }
+      const uint32_t off = (c - fr) * PP_CHUNK;
+      const uint64_t* src = pa.buf + (size_t)(q * PART_REPL + (uint32_t)r) * pa.region_cap + off;
+      const uint32_t m = min((uint32_t)PP_CHUNK, nr - off);
       uint64_t cn[PP_BATCH];
       uint32_t vm = 0;
 #pragma unroll
       for (int i = 0; i < PP_BATCH; ++i) {
-        const uint32_t j = r + (uint32_t)i * 256 + (uint32_t)tid;
-        cn[i] = nx[i];
+        const uint32_t j = (uint32_t)i * 256 + (uint32_t)tid;
+        cn[i] = j < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
         vm |= j < m ? 1u << i : 0u;
-        const uint32_t jn = j + PP_BATCH * 256;
-        nx[i] = jn < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + jn)) : 0ull;
       }
       probeN<OP, PP_QUEUE, PP_BATCH>(cn, vm, T, inserted, &s_wq);
+      if (PP_QUEUE && OP == PG_OP_UPDATE) drain_walks(&s_wq, T);
+      __syncthreads();  // the next chunk id has landed; everybody is done reading this one
     }
-    if (PP_QUEUE && OP == PG_OP_UPDATE) drain_walks(&s_wq, T);
+    __syncthreads();  // s_fill[cur ^ 1] complete, s_fill[cur] and s_chunk free for the next partition
   }
   for (int o = 16; o > 0; o >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
   if ((tid & 31) == 0 && inserted) atomicAdd(T.scalars + SC_DISTINCT, (unsigned long long)inserted);
@@ -1088,7 +1074,7 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
 // third of the free HBM, at most 24 GiB), PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
 // PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning.
 static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 40u << 10) << 10; }
-constexpr size_t PART_CURSOR_WORDS = (size_t)MAX_PARTS * PART_REPL * CURSOR_STRIDE;
+constexpr size_t PART_CURSOR_WORDS = (size_t)MAX_PARTS * PART_REPL * CURSOR_STRIDE;   // followed by MAX_PARTS work counters
 
 // decides whether this pass is partitioned; sizes the buffers; `super` = text bytes per probe pass
 static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is_fastq, PartArgs& pa, bool& use, uint64_t& super) {
@@ -1126,15 +1112,14 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is
     c->part_buf_cap = need;
   }
   if (!c->d_part_cursor) {
-    PG_CUDA(cudaMalloc((void**)&c->d_part_cursor, (PART_CURSOR_WORDS + (size_t)MAX_PARTS * PART_REPL + 16) * sizeof(uint32_t)));
-    PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, PART_CURSOR_WORDS * sizeof(uint32_t), c->stream));
+    PG_CUDA(cudaMalloc((void**)&c->d_part_cursor, (PART_CURSOR_WORDS + MAX_PARTS + 1) * sizeof(uint32_t)));
+    PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (PART_CURSOR_WORDS + MAX_PARTS + 1) * sizeof(uint32_t), c->stream));
   }
   pa.buf = reinterpret_cast<uint64_t*>(c->d_part_buf);
   pa.cursor = c->d_part_cursor;
-  pa.item_start = c->d_part_cursor + PART_CURSOR_WORDS;
+  pa.work = c->d_part_cursor + PART_CURSOR_WORDS;
   pa.region_cap = (uint32_t)region;
   pa.n_parts = n_parts;
-  pa.item = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(env_u64("PG_COUNT_PROBE_ITEM", PP_ITEM), 256), 1u << 20);
   // text per pass the regions are sized for (the excess of an over-full region is probed directly, so an underestimate
   // of the k-mer density costs speed, not correctness)
   super = std::max<uint64_t>((uint64_t)((double)(region * n_regions) / (density * slack)), 1ull << 20);
@@ -1157,16 +1142,21 @@ static int part_flush(pg_counter* c, const PartArgs& pa, int op) {
     }
     PG_CUDA(cudaEventRecord(c->ev_probe[2 * c->n_probe], c->stream));
   }
-  part_items_kernel<<<1, 1024, 0, c->stream>>>(pa);
-  if (op == PG_OP_COUNT) probe_parts_kernel<PG_OP_COUNT><<<sms * 6, 256, 0, c->stream>>>(pa, T);
-  else probe_parts_kernel<PG_OP_UPDATE><<<sms * 6, 256, 0, c->stream>>>(pa, T);
-  count_launch(2);
+  // exactly the co-resident grid: every CTA is on the machine, so they move through the partitions together
+  int occ = 0;
+  if (op == PG_OP_COUNT) PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_parts_kernel<PG_OP_COUNT>, 256, 0));
+  else PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_parts_kernel<PG_OP_UPDATE>, 256, 0));
+  const int grid = sms * std::max(occ, 1);
+  if (op == PG_OP_COUNT) probe_parts_kernel<PG_OP_COUNT><<<grid, 256, 0, c->stream>>>(pa, T);
+  else probe_parts_kernel<PG_OP_UPDATE><<<grid, 256, 0, c->stream>>>(pa, T);
+  count_launch();
   PG_CUDA(cudaGetLastError());
   if (timed) {
     PG_CUDA(cudaEventRecord(c->ev_probe[2 * c->n_probe + 1], c->stream));
     ++c->n_probe;
   }
   PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (size_t)pa.n_parts * PART_REPL * CURSOR_STRIDE * sizeof(uint32_t), c->stream));
+  PG_CUDA(cudaMemsetAsync(pa.work, 0, (size_t)pa.n_parts * sizeof(uint32_t), c->stream));
   return PG_OK;
 }
 
@@ -1214,6 +1204,7 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   PG_TRY(part_setup(c, len, op, direct, is_fastq, pa, parted, super));
   if (parted) step = std::min<uint64_t>(step, super);  // a chunk never exceeds what the regions are sized for
   if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (size_t)pa.n_parts * PART_REPL * CURSOR_STRIDE * sizeof(uint32_t), c->stream));
+  if (parted) PG_CUDA(cudaMemsetAsync(pa.work, 0, (size_t)pa.n_parts * sizeof(uint32_t), c->stream));
   uint64_t scattered = 0;  // text bytes scattered into the partition buffers since the last flush
   for (uint64_t off = 0; off < len; off += step) {
     const uint64_t n = std::min<uint64_t>(step, len - off);

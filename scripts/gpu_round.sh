@@ -47,7 +47,7 @@ print("slice_kb", $kb, "step_ms", round(d["ms_per_step"],1), "update_ms", round(
 EOF
   done;;
 sweep_items)
-  for cfg in "16384 1024" "16384 2048" "40960 1024" "40960 4096" "98304 1024" "98304 8192" "8192 1024"; do
+  for cfg in ${SWEEP:-"16384 0" "24576 0" "40960 0" "65536 0" "98304 0"}; do
     set -- $cfg
     PG_COUNT_PART_KB=$1 PG_COUNT_PROBE_ITEM=$2 PG_BENCH_E2E_STEPS=0 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > $out/bench_sw_$1_$2_$tag.json 2> $out/bench_sw_$1_$2_$tag.err
     python - <<EOF

@@ -40,6 +40,8 @@ def launches(path):
         except ValueError:
             continue
         k = d["Kernel Name"].split("(")[0][:70]
+        if "pg::" not in k:
+            continue   # torch kernels of the synthetic data generator (bench tooling), not the library
         agg[k][0] += 1
         agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
