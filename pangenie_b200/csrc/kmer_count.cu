@@ -529,7 +529,8 @@ __device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
   return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
 }
 
-constexpr size_t SCATTER_SMEM = (size_t)(MAX_PARTS + 1) * 4 + (size_t)CT_TILE * 4 + (size_t)CT_TILE * 8;  // s_cnt + s_info + s_kmer
+constexpr size_t SCATTER_SMEM_MAX = (size_t)CT_TILE * 4 + (size_t)(MAX_PARTS + 1) * 4;  // s_info + s_cnt at the largest partition count
+static inline size_t scatter_smem(uint32_t n_parts) { return (size_t)CT_TILE * 4 + (size_t)(n_parts + 1) * 4; }
 constexpr int PK_WORDS = CT_TILE / 16 + 4;  // packed codes: 16 symbols per word (+ read-ahead padding)
 constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per word
 
@@ -545,12 +546,12 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   __shared__ uint32_t s_nb[NB_WORDS];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
-  // scatter mode (dynamic shared memory, 52 KB): per-partition counts -> write cursors, (partition, rank) and the canonical
-  // k-mer of every start position, so each k-mer costs ONE shared-memory atomic and is extracted once
+  // scatter mode (dynamic shared memory): (partition, rank) of every start position and the per-partition counts -> write
+  // cursors, so each k-mer costs ONE shared-memory atomic.  The k-mer itself is extracted again in the append pass: parking it
+  // in shared memory (32 KB more) cost two resident CTAs per SM, and this kernel lives on occupancy (issue slots 31% busy).
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_dyn);                                            // [MAX_PARTS + 1]
-  uint32_t* s_info = s_cnt + (MAX_PARTS + 1);                                                      // [CT_TILE]
-  unsigned long long* s_kmer = reinterpret_cast<unsigned long long*>(s_info + CT_TILE);            // [CT_TILE]
+  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_dyn);                                           // [CT_TILE]
+  uint32_t* s_cnt = s_info + CT_TILE;                                                              // [n_parts]
   unsigned long long* scalars = T.scalars;
   if (SCATTER)
     for (uint32_t i = threadIdx.x; i < pa.n_parts; i += CT_THREADS) s_cnt[i] = 0;
@@ -739,7 +740,6 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
         const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
         if (p < n_owned_syms) {
           s_info[p] = ok[u] ? ((part[u] << 12) | rank[u]) : 0xffffffffu;
-          if (ok[u]) s_kmer[p] = can[u];
         }
         nk += ok[u] ? 1u : 0u;
       }
@@ -780,7 +780,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
         const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
         const bool ok = info[u] != 0xffffffffu;
         base[u] = ok ? s_cnt[info[u] >> 12] : 0u;
-        can[u] = ok ? s_kmer[p] : 0ull;
+        kmer_at(min(p, n_owned_syms - 1u), can[u]);
       }
 #pragma unroll
       for (int u = 0; u < SB; ++u) {
@@ -1049,12 +1049,13 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
   if (pa) {
     static bool attr_set[64] = {};   // per device
     if (c->device < 64 && !attr_set[c->device]) {
-      PG_CUDA(cudaFuncSetAttribute(count_tile_kernel<PG_OP_COUNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
-      PG_CUDA(cudaFuncSetAttribute(count_tile_kernel<PG_OP_UPDATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
+      PG_CUDA(cudaFuncSetAttribute(count_tile_kernel<PG_OP_COUNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM_MAX));
+      PG_CUDA(cudaFuncSetAttribute(count_tile_kernel<PG_OP_UPDATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM_MAX));
       attr_set[c->device] = true;
     }
-    if (op == PG_OP_COUNT) count_tile_kernel<PG_OP_COUNT, true><<<n_tiles, CT_THREADS, SCATTER_SMEM, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
-    else count_tile_kernel<PG_OP_UPDATE, true><<<n_tiles, CT_THREADS, SCATTER_SMEM, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
+    const size_t smem = scatter_smem(pa->n_parts);
+    if (op == PG_OP_COUNT) count_tile_kernel<PG_OP_COUNT, true><<<n_tiles, CT_THREADS, smem, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
+    else count_tile_kernel<PG_OP_UPDATE, true><<<n_tiles, CT_THREADS, smem, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, *pa);
   } else {
     switch (op) {
       case PG_OP_COUNT: count_tile_kernel<PG_OP_COUNT, false><<<n_tiles, CT_THREADS, 0, c->stream>>>(d_text, n, n_avail, is_fastq, meta, c->k, T, none); break;
