@@ -162,11 +162,15 @@ struct pg_counter {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   // streaming scratch
-  static constexpr int NSTAGE = 4;                  // staging ring: copies run ahead of the counting kernels
-  char* d_stage[NSTAGE] = {};
+  // staging ring: copies run ahead of the counting kernels.  NSTAGE buffers for sources the host has to touch (pageable
+  // memory, files: the host copy is the bottleneck anyway); up to NSTAGE_DEEP for pinned host text, so the PCIe stream keeps
+  // running while a probe pass of the partitioned mode occupies the compute stream (buffers are allocated on first use)
+  static constexpr int NSTAGE = 4;
+  static constexpr int NSTAGE_DEEP = 192;           // x 16 MiB = 3 GiB of device staging at most
+  char* d_stage[NSTAGE_DEEP] = {};
   char* h_stage[NSTAGE] = {};
-  cudaEvent_t stage_free[NSTAGE] = {};   // kernel finished reading d_stage[i]
-  cudaEvent_t stage_ready[NSTAGE] = {};  // H2D into d_stage[i] finished
+  cudaEvent_t stage_free[NSTAGE_DEEP] = {};   // kernel finished reading d_stage[i]
+  cudaEvent_t stage_ready[NSTAGE_DEEP] = {};  // H2D into d_stage[i] finished
   int stage_next = 0;                    // ring position (persists across feeds so consecutive feeds overlap)
   uint32_t* d_tile_meta = nullptr;                  // per-tile scan scratch
   size_t tile_meta_cap = 0;

@@ -804,73 +804,86 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   }
 }
 
-// Probe pass over the filled partition buffers.  ALL CTAs of the (co-resident) grid march through the partitions together:
+// Probe pass over the filled partition buffers.  ALL warps of the (co-resident) grid march through the partitions together:
 // within a partition the k-mers of its PART_REPL regions are handed out in chunks of PP_CHUNK from a per-partition work
-// counter, and a CTA moves on to the next partition only when the current one has nothing left to hand out - so at any
+// counter, and a warp moves on to the next partition only when the current one has nothing left to hand out - so at any
 // moment the whole GPU probes one or two neighbouring table slices, and the working set that has to stay in the L2 is the
 // slice size, whatever the number of k-mers per pass.  (Dealing work items statically - round-robin over the grid - lets
 // the persistent CTAs drift apart over the thousands of items of a pass until they span hundreds of MB of table; measured
-// at configs[2] with 16 MB slices: 234 GB of DRAM reads per pass of 1.8 G k-mers, L2 hit rate 22%, i.e. every probe a burst.)
-constexpr int PP_CHUNK = 1024;
-constexpr bool PP_QUEUE = false;  // park overflow walks in a shared-memory queue (barriers per item) or walk in place
-constexpr int PP_BATCH = 4;  // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
-static_assert(PP_CHUNK == PP_BATCH * 256, "one chunk = one round of the CTA");
+// at configs[2] with 16 MB slices: 234 GB of DRAM reads per pass of 1.8 G k-mers, L2 hit rate 22%, i.e. every probe a burst.
+// With the hand-out: 32.5 GB, hit rate 58%.)
+// Warps are autonomous - no CTA barrier anywhere (the per-chunk barrier of the first hand-out version was 24% of its stall
+// samples): lane 0 takes the chunk ids, one chunk ahead; the k-mers of the next round are requested before the current
+// round is probed; the counts are incremented with plain RED (a __match_any aggregation per k-mer was another 18%; a
+// k-mer that is hot in the read set costs its partition's warps same-address REDs, which the L2 takes at about one per clock).
+constexpr int PP_CHUNK = 1024;    // k-mers per chunk (8 rounds of a warp): ~14 k hand-outs per partition sweep at configs[2]
+constexpr bool PP_QUEUE = false;  // (direct kernel experiments) park overflow walks in a shared-memory queue
+constexpr int PP_BATCH = 4;       // k-mers per thread per round (cfg3s UPDATE pass: 2 -> 49.5 ms, 4 -> 42.8 ms, 8 -> 50.6 ms)
+constexpr int PP_ROUND = PP_BATCH * 32;
+static_assert(PP_CHUNK % PP_ROUND == 0, "a chunk is a whole number of warp rounds");
 
 template <int OP>
-__global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, const TableRef T) {
-  __shared__ WalkQueue s_wq;
-  __shared__ uint32_t s_fill[2][PART_REPL];  // k-mers in the regions of the current partition (double-buffered)
-  __shared__ uint32_t s_chunk[2];             // chunk being probed / the next one, already requested
-  const int tid = threadIdx.x;
-  if (tid == 0) s_wq.n = 0;
+__global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, TableRef T) {
+  const uint32_t lane = threadIdx.x & 31u;
+  T.flags |= 1u;  // plain atomics
   uint32_t inserted = 0;
-  if (tid < PART_REPL) s_fill[0][tid] = min(pa.cursor[(size_t)tid * CURSOR_STRIDE], pa.region_cap);
-  __syncthreads();
   for (uint32_t q = 0; q < pa.n_parts; ++q) {
-    const int cur = (int)(q & 1u);
-    // fills of the next partition on their way while this one is probed
-    if (tid < PART_REPL && q + 1 < pa.n_parts)
-      s_fill[cur ^ 1][tid] = min(pa.cursor[(size_t)((q + 1) * PART_REPL + tid) * CURSOR_STRIDE], pa.region_cap);
-    // chunk c of the partition = chunk (c - first[r]) of region r
-    uint32_t first[PART_REPL + 1];
-    first[0] = 0;
+    // lane r < PART_REPL: fill of region (q, r) and the first chunk id of that region within the partition
+    uint32_t fill = 0;
+    if (lane < PART_REPL) fill = min(pa.cursor[(size_t)(q * PART_REPL + lane) * CURSOR_STRIDE], pa.region_cap);
+    const uint32_t nch = (fill + PP_CHUNK - 1) / PP_CHUNK;
+    uint32_t first = nch;  // inclusive scan over the lanes, then exclusive
 #pragma unroll
-    for (int r = 0; r < PART_REPL; ++r) first[r + 1] = first[r] + (s_fill[cur][r] + PP_CHUNK - 1) / PP_CHUNK;
-    const uint32_t total = first[PART_REPL];
-    if (tid == 0) s_chunk[0] = total ? atomicAdd(pa.work + q, 1u) : 0u;
-    __syncthreads();
-    for (uint32_t k = 0;; ++k) {
-      const uint32_t c = s_chunk[k & 1u];
-      if (c >= total) break;
-      if (tid == 0) s_chunk[(k + 1u) & 1u] = atomicAdd(pa.work + q, 1u);   // in flight while this chunk is probed
-      int r = 0;
-#pragma unroll
-      for (int u = 1; u < PART_REPL; ++u) r += c >= first[u] ? 1 : 0;   // regions without chunks share their successor's start
-      uint32_t fr = 0, nr = 0;
-#pragma unroll
-      for (int u = 0; u < PART_REPL; ++u) {   // (register array indexed by a loop-carried value: select instead of local memory)
-        fr = u == r ? first[u] : fr;
-        nr = u == r ? s_fill[cur][u] : nr;
-      }
+    for (int o = 1; o < PART_REPL; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, first, o);
+      if ((int)lane >= o) first += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, first, PART_REPL - 1);
+    first -= nch;
+    if (total == 0) continue;
+    uint32_t c = 0, c_next = 0;
+    if (lane == 0) {
+      c = atomicAdd(pa.work + q, 1u);
+      if (c < total) c_next = atomicAdd(pa.work + q, 1u);
+    }
+    c = __shfl_sync(0xffffffffu, c, 0);
+    while (c < total) {
+      // region of chunk c: the last region whose first chunk id is <= c and that has chunks at all
+      const uint32_t owners = __ballot_sync(0xffffffffu, lane < PART_REPL && nch > 0 && first <= c);
+      const int r = 31 - __clz((int)owners);
+      const uint32_t fr = __shfl_sync(0xffffffffu, first, r), nr = __shfl_sync(0xffffffffu, fill, r);
       const uint32_t off = (c - fr) * PP_CHUNK;
       const uint64_t* src = pa.buf + (size_t)(q * PART_REPL + (uint32_t)r) * pa.region_cap + off;
       const uint32_t m = min((uint32_t)PP_CHUNK, nr - off);
-      uint64_t cn[PP_BATCH];
-      uint32_t vm = 0;
+      uint64_t nx[PP_BATCH];
 #pragma unroll
       for (int i = 0; i < PP_BATCH; ++i) {
-        const uint32_t j = (uint32_t)i * 256 + (uint32_t)tid;
-        cn[i] = j < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
-        vm |= j < m ? 1u << i : 0u;
+        const uint32_t j = (uint32_t)i * 32u + lane;
+        nx[i] = j < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + j)) : 0ull;
       }
-      probeN<OP, PP_QUEUE, PP_BATCH>(cn, vm, T, inserted, &s_wq);
-      if (PP_QUEUE && OP == PG_OP_UPDATE) drain_walks(&s_wq, T);
-      __syncthreads();  // the next chunk id has landed; everybody is done reading this one
+#pragma unroll 1
+      for (uint32_t rd = 0; rd < m; rd += PP_ROUND) {
+        uint64_t cn[PP_BATCH];
+        uint32_t vm = 0;
+#pragma unroll
+        for (int i = 0; i < PP_BATCH; ++i) {
+          const uint32_t j = rd + (uint32_t)i * 32u + lane;
+          cn[i] = nx[i];
+          vm |= j < m ? 1u << i : 0u;
+          const uint32_t jn = j + PP_ROUND;
+          nx[i] = jn < m ? __ldcs(reinterpret_cast<const unsigned long long*>(src + jn)) : 0ull;
+        }
+        probeN<OP, false, PP_BATCH>(cn, vm, T, inserted, nullptr);
+      }
+      // the id requested one chunk ago has long landed; request the one after it
+      uint32_t c_after = 0;
+      if (lane == 0 && c_next < total) c_after = atomicAdd(pa.work + q, 1u);
+      c = __shfl_sync(0xffffffffu, c_next, 0);
+      c_next = lane == 0 ? (c < total ? c_after : c) : 0u;
     }
-    __syncthreads();  // s_fill[cur ^ 1] complete, s_fill[cur] and s_chunk free for the next partition
   }
   for (int o = 16; o > 0; o >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
-  if ((tid & 31) == 0 && inserted) atomicAdd(T.scalars + SC_DISTINCT, (unsigned long long)inserted);
+  if (lane == 0 && inserted) atomicAdd(T.scalars + SC_DISTINCT, (unsigned long long)inserted);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -999,10 +1012,12 @@ __global__ void __launch_bounds__(256) canonicalize_kernel(KmerBucket* __restric
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int ensure_stage(pg_counter* c, bool need_host) {
-  for (int i = 0; i < pg_counter::NSTAGE; ++i) {
+static int ensure_stage(pg_counter* c, int ring, bool need_host) {
+  for (int i = 0; i < ring; ++i) {
     if (!c->d_stage[i]) PG_CUDA(cudaMalloc((void**)&c->d_stage[i], STAGE_BYTES + 256));
-    if (need_host && !c->h_stage[i]) PG_CUDA(cudaMallocHost((void**)&c->h_stage[i], STAGE_BYTES + 256));
+    if (!c->stage_free[i]) PG_CUDA(cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming));
+    if (!c->stage_ready[i]) PG_CUDA(cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming));
+    if (need_host && i < pg_counter::NSTAGE && !c->h_stage[i]) PG_CUDA(cudaMallocHost((void**)&c->h_stage[i], STAGE_BYTES + 256));
   }
   return PG_OK;
 }
@@ -1074,13 +1089,14 @@ static int launch_chunk(pg_counter* c, const char* d_text, uint64_t n, uint64_t 
 // allow.  Knobs: PG_COUNT_SUPER_MB caps the text per pass (test knob), PG_COUNT_PART_BUF_MB the buffer memory (default: a
 // third of the free HBM, at most 24 GiB), PG_COUNT_PART_KB = table bytes per partition in KiB (0 disables partitioning),
 // PG_COUNT_PART_MIN_TEXT = smallest text (bytes) that is worth partitioning.
-static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 40u << 10) << 10; }
+static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 96u << 10) << 10; }
 constexpr size_t PART_CURSOR_WORDS = (size_t)MAX_PARTS * PART_REPL * CURSOR_STRIDE;   // followed by MAX_PARTS work counters
 
 // decides whether this pass is partitioned; sizes the buffers; `super` = text bytes per probe pass
 static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is_fastq, PartArgs& pa, bool& use, uint64_t& super) {
   use = false;
-  // text streamed over PCIe arrives slower than the direct kernel counts it: partitioning would only add a tail
+  // `resident`: device text, or pinned host text behind a deep staging ring (the PCIe stream runs on while a probe pass
+  // occupies the compute stream).  Text the host has to copy first arrives too slowly for partitioning to matter.
   if (!resident && !env_u64("PG_COUNT_PART_STAGED", 0)) return PG_OK;
   const uint64_t slice = part_slice_bytes();
   const uint64_t table_bytes = (c->capacity >> 2) * sizeof(KmerBucket);
@@ -1196,13 +1212,18 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   if (op != PG_OP_PRIME) c->n_probe = 0;
   PG_CUDA(cudaEventRecord(ev0, c->stream));
   const bool direct = on_device && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  if (!direct && len) PG_TRY(ensure_stage(c, !on_device && !pinned));
+  // ring depth: pinned host text may run far ahead of the kernels (PG_COUNT_RING caps it: test knob)
+  int ring = pg_counter::NSTAGE;
+  if (pinned) ring = (int)std::max<uint64_t>(pg_counter::NSTAGE, std::min<uint64_t>(std::min<uint64_t>(pg_counter::NSTAGE_DEEP, env_u64("PG_COUNT_RING", pg_counter::NSTAGE_DEEP)),
+                                                                                  (len + STAGE_BYTES - 1) / STAGE_BYTES));
+  if (!direct && len) PG_TRY(ensure_stage(c, ring, !on_device && !pinned));
+  if (c->stage_next >= ring) c->stage_next = 0;
   uint64_t step = direct ? CHUNK_BYTES : STAGE_BYTES;
   PartArgs pa;
   memset(&pa, 0, sizeof(pa));
   bool parted = false;
   uint64_t super = 0;
-  PG_TRY(part_setup(c, len, op, direct, is_fastq, pa, parted, super));
+  PG_TRY(part_setup(c, len, op, direct || (pinned && ring > pg_counter::NSTAGE), is_fastq, pa, parted, super));
   if (parted) step = std::min<uint64_t>(step, super);  // a chunk never exceeds what the regions are sized for
   if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (size_t)pa.n_parts * PART_REPL * CURSOR_STRIDE * sizeof(uint32_t), c->stream));
   if (parted) PG_CUDA(cudaMemsetAsync(pa.work, 0, (size_t)pa.n_parts * sizeof(uint32_t), c->stream));
@@ -1216,7 +1237,7 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
       d_text = src + off;
     } else {
       buf = c->stage_next;
-      c->stage_next = (c->stage_next + 1) % pg_counter::NSTAGE;
+      c->stage_next = (c->stage_next + 1) % ring;
       // wait until the kernels that last read this staging buffer are done
       PG_CUDA(cudaEventSynchronize(c->stage_free[buf]));
       if (on_device) {
@@ -1353,10 +1374,6 @@ extern "C" pg_counter* pg_count_new(uint32_t k, uint64_t max_distinct, int devic
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  for (int i = 0; i < pg_counter::NSTAGE; ++i) {
-    if ((e = cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-  }
   if ((e = cudaEventCreate(&c->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&c->ev_t1)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev_p0)) != cudaSuccess || (e = cudaEventCreate(&c->ev_p1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc((void**)&c->slots, (c->capacity / 4) * sizeof(KmerBucket))) != cudaSuccess) return bail("cudaMalloc(slots)", e);
@@ -1384,9 +1401,9 @@ extern "C" void pg_count_destroy(pg_counter* c) {
   if (c->ev_p0) cudaEventDestroy(c->ev_p0);
   if (c->ev_p1) cudaEventDestroy(c->ev_p1);
   for (cudaEvent_t ev : c->ev_probe) cudaEventDestroy(ev);
-  for (int i = 0; i < pg_counter::NSTAGE; ++i) {
+  for (int i = 0; i < pg_counter::NSTAGE_DEEP; ++i) {
     if (c->d_stage[i]) cudaFree(c->d_stage[i]);
-    if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    if (i < pg_counter::NSTAGE && c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
     if (c->stage_ready[i]) cudaEventDestroy(c->stage_ready[i]);
   }
