@@ -114,6 +114,12 @@ struct __align__(64) KmerBucket {
   uint32_t pad[4];
 };
 
+/** The four keys of a bucket with ONE 256-bit load (LDG.E.256, new with sm_100: the key sector is 32 bytes, so a probe is a
+ *  single request to the L2 instead of two 128-bit ones). */
+__device__ __forceinline__ void ld_bucket_keys(const KmerBucket* b, ulonglong2& ka, ulonglong2& kb) {
+  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(ka.x), "=l"(ka.y), "=l"(kb.x), "=l"(kb.y) : "l"(b->key));
+}
+
 /** canonicalise + look up; 0 if absent (getKmerAbundance, reference src/jellyfishcounter.cpp:87-104) */
 __device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, const KmerBucket* __restrict__ tab, uint64_t cap,
                                                  uint32_t q, uint32_t sh) {
@@ -122,8 +128,8 @@ __device__ __forceinline__ uint32_t table_lookup(uint64_t code, uint32_t k, cons
   uint64_t b = home_slot(can, q, sh) >> 2;
   const uint64_t nb = cap >> 2;
   for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
-    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&tab[b].key[0]);
-    const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&tab[b].key[2]);
+    ulonglong2 k01, k23;
+    ld_bucket_keys(&tab[b], k01, k23);
     if (k01.x == can) return tab[b].cnt[0];
     if (k01.x == EMPTY_KEY) return 0;
     if (k01.y == can) return tab[b].cnt[1];

@@ -335,8 +335,8 @@ struct WalkQueue {
 // walks from bucket b in a STATIC table; counts the k-mer if present
 __device__ __noinline__ void walk_count(uint64_t kmer, uint64_t b, const TableRef& T) {
   for (uint32_t probes = 0; probes < (1u << 20); ++probes) {
-    const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&T.tab[b].key[0]);
-    const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&T.tab[b].key[2]);
+    ulonglong2 ka, kb;
+    ld_bucket_keys(&T.tab[b], ka, kb);
     const int pos = match_pos(ka, kb, kmer);
     if (pos >= 0) {
       atomicAdd(&T.tab[b].cnt[pos], 1u);
@@ -371,8 +371,8 @@ __device__ __forceinline__ void probeN(const uint64_t (&cn)[N], uint32_t vm, con
   for (int i = 0; i < N; ++i) {
     const bool v = (vm >> i) & 1u;
     bkt[i] = home_slot(cn[i], T.cap_q, T.cap_sh) >> 2;
-    ka[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]) : make_ulonglong2(0, 0);
-    kb[i] = v ? *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]) : make_ulonglong2(0, 0);
+    ka[i] = kb[i] = make_ulonglong2(0, 0);
+    if (v) ld_bucket_keys(&tab[bkt[i]], ka[i], kb[i]);
   }
   uint32_t hitm = 0, need = 0;  // bit i: k-mer i found, its slot is in bkt[i] / continue in bucket bkt[i] (UPDATE) or CAS pending
   unsigned long long cas_old[N];
@@ -450,10 +450,7 @@ __device__ __forceinline__ void probeN(const uint64_t (&cn)[N], uint32_t vm, con
     while (need) {
 #pragma unroll
       for (int i = 0; i < N; ++i)
-        if ((need >> i) & 1u) {
-          ka[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[0]);
-          kb[i] = *reinterpret_cast<const ulonglong2*>(&tab[bkt[i]].key[2]);
-        }
+        if ((need >> i) & 1u) ld_bucket_keys(&tab[bkt[i]], ka[i], kb[i]);
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if ((need >> i) & 1u) {
@@ -823,7 +820,7 @@ constexpr int PP_ROUND = PP_BATCH * 32;
 static_assert(PP_CHUNK % PP_ROUND == 0, "a chunk is a whole number of warp rounds");
 
 template <int OP>
-__global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 3 : 2) probe_parts_kernel(const PartArgs pa, TableRef T) {
+__global__ void __launch_bounds__(256, PP_BATCH == 2 ? 5 : PP_BATCH == 4 ? 4 : 2) probe_parts_kernel(const PartArgs pa, TableRef T) {
   const uint32_t lane = threadIdx.x & 31u;
   T.flags |= 1u;  // plain atomics
   uint32_t inserted = 0;
