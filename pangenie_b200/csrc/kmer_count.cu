@@ -526,8 +526,8 @@ __device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
   return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
 }
 
-constexpr size_t SCATTER_SMEM_MAX = (size_t)CT_TILE * 4 + (size_t)(MAX_PARTS + 1) * 4;  // s_info + s_cnt at the largest partition count
-static inline size_t scatter_smem(uint32_t n_parts) { return (size_t)CT_TILE * 4 + (size_t)(n_parts + 1) * 4; }
+constexpr size_t SCATTER_SMEM_MAX = (size_t)(MAX_PARTS + 1) * 4;  // s_cnt at the largest partition count
+static inline size_t scatter_smem(uint32_t n_parts) { return (size_t)(n_parts + 1) * 4; }
 constexpr int PK_WORDS = CT_TILE / 16 + 4;  // packed codes: 16 symbols per word (+ read-ahead padding)
 constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per word
 
@@ -543,12 +543,10 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   __shared__ uint32_t s_nb[NB_WORDS];
   __shared__ uint32_t s_warp[40];
   __shared__ int s_warp_i[32];
-  // scatter mode (dynamic shared memory): (partition, rank) of every start position and the per-partition counts -> write
-  // cursors, so each k-mer costs ONE shared-memory atomic.  The k-mer itself is extracted again in the append pass: parking it
-  // in shared memory (32 KB more) cost two resident CTAs per SM, and this kernel lives on occupancy (issue slots 31% busy).
+  // scatter mode (dynamic shared memory): the per-partition counts of the tile -> write cursors; each k-mer costs ONE
+  // shared-memory atomic (it returns the rank within the partition)
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_dyn);                                           // [CT_TILE]
-  uint32_t* s_cnt = s_info + CT_TILE;                                                              // [n_parts]
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_dyn);                                            // [n_parts]
   unsigned long long* scalars = T.scalars;
   if (SCATTER)
     for (uint32_t i = threadIdx.x; i < pa.n_parts; i += CT_THREADS) s_cnt[i] = 0;
@@ -711,81 +709,89 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
       probeN<OP, false, 4>(cn, vm, T, inserted, nullptr);
     }
   } else {
+    // Every thread takes KPT CONSECUTIVE start positions: the packed stream and the not-a-base stream of its window are
+    // loaded once (7 shared-memory loads for 8 k-mers instead of 5 per k-mer), the forward k-mers are constant-shift
+    // extractions from that window, the reverse complements roll (the newest base of k-mer j is its last two bits), and the
+    // canonical k-mers stay in registers between ranking and appending.  Per sub-round of KPT * 256 positions:
     // (1) rank my k-mers within their partition (the shared-memory atomic returns the rank), (2) reserve one contiguous
-    // range per partition for the whole tile in this tile's replica region, (3) append.  A region that is full (skewed
-    // data) sends its k-mers straight to the table.
-    // Four start positions per thread and round: the passes are chains of dependent shared-memory operations (measured:
-    // 38% of the stall samples on the short scoreboard with one position in flight), so the loads / atomics of four
-    // independent positions are issued together.
+    // range per partition in this tile's replica region, (3) append.  A region that is full (skewed data) sends its
+    // k-mers straight to the table.  A FASTQ tile (about half of its bytes are sequence) is one sub-round.
+    constexpr int KPT = 8;
     const uint32_t repl = blockIdx.x % PART_REPL;
-    constexpr int SB = 4;
+    const int nq = (int)((pa.n_parts + CT_THREADS - 1) / CT_THREADS);
+    constexpr int QMAX = (MAX_PARTS + CT_THREADS) / CT_THREADS;
+    const uint32_t rc_shift = 2u * (k - 1u);
 #pragma unroll 1
-    for (uint32_t p0 = (uint32_t)tid; p0 < n_owned_syms; p0 += SB * CT_THREADS) {
-      uint64_t can[SB];
-      uint32_t part[SB], rank[SB];
-      bool ok[SB];
-#pragma unroll
-      for (int u = 0; u < SB; ++u) {
-        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
-        ok[u] = kmer_at(min(p, n_owned_syms - 1u), can[u]) && p < n_owned_syms;   // (clamped: no reads past the packed stream)
-        part[u] = part_of(can[u], pa.n_parts);
+    for (uint32_t sub = 0; sub < n_owned_syms; sub += KPT * CT_THREADS) {
+      if (sub) {  // second sub-round (FASTA tiles): fresh counts
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < pa.n_parts; i += CT_THREADS) s_cnt[i] = 0;
+        __syncthreads();
       }
+      const uint32_t p0 = sub + (uint32_t)tid * KPT;   // multiple of 8
+      uint64_t can[KPT];
+      uint32_t info[KPT];                              // partition << 12 | rank, 0xffffffff: no k-mer
+      uint32_t okm = 0;
+      if (p0 < n_owned_syms) {
+        const uint32_t wi = p0 >> 4, sh = 2u * (p0 & 15u);          // sh is 0 or 16
+        const uint32_t w0 = s_pk[wi], w1 = s_pk[wi + 1], w2 = s_pk[wi + 2], w3 = s_pk[wi + 3];
+        // 128-bit window whose top symbol is position p0
+        const uint64_t a_hi = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+        const uint64_t a_lo = ((uint64_t)__funnelshift_l(w3, w2, sh) << 32) | (uint64_t)(w3 << sh);
+        const uint32_t ni = p0 >> 5, nsh = p0 & 31u;               // nsh is 0, 8, 16 or 24
+        const uint32_t m0 = s_nb[ni], m1 = s_nb[ni + 1], m2 = s_nb[ni + 2];
+        const uint64_t nbw = ((uint64_t)__funnelshift_l(m1, m0, nsh) << 32) | __funnelshift_l(m2, m1, nsh);  // bit 63 = position p0
+        uint64_t rc = 0;
 #pragma unroll
-      for (int u = 0; u < SB; ++u) rank[u] = ok[u] ? atomicAdd(&s_cnt[part[u]], 1u) : 0u;   // rank < 4096 = CT_TILE
-#pragma unroll
-      for (int u = 0; u < SB; ++u) {
-        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
-        if (p < n_owned_syms) {
-          s_info[p] = ok[u] ? ((part[u] << 12) | rank[u]) : 0xffffffffu;
+        for (int j = 0; j < KPT; ++j) {
+          const uint64_t top = j == 0 ? a_hi : ((a_hi << (2 * j)) | (a_lo >> (64 - 2 * j)));
+          const uint64_t fwd = top >> kshift;
+          rc = j == 0 ? revcomp_2bit(fwd, k) : ((rc >> 2) | ((3ull - (fwd & 3ull)) << rc_shift));
+          can[j] = fwd < rc ? fwd : rc;
+          const bool bad = ((nbw << j) >> (64u - k)) != 0ull;
+          const uint32_t p = p0 + (uint32_t)j;
+          okm |= (p < n_owned_syms && p + k <= n_syms && !bad) ? 1u << j : 0u;
         }
-        nk += ok[u] ? 1u : 0u;
-      }
-    }
-    __syncthreads();
-    {
-      // one reservation per non-empty partition; all atomics of a thread are in flight together
-      constexpr int QMAX = (MAX_PARTS + CT_THREADS) / CT_THREADS;
-      const int nq = (int)((pa.n_parts + CT_THREADS - 1) / CT_THREADS);
-      uint32_t basev[QMAX];
+      } else {
 #pragma unroll
-      for (int u = 0; u < QMAX; ++u) {
-        const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
-        basev[u] = 0;
-        if (u < nq && q < pa.n_parts) {
-          const uint32_t cnt = s_cnt[q];
-          if (cnt) basev[u] = atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cnt);
+        for (int j = 0; j < KPT; ++j) can[j] = 0;
+      }
+      uint32_t part[KPT];
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) part[j] = part_of(can[j], pa.n_parts);
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) info[j] = ((okm >> j) & 1u) ? ((part[j] << 12) | atomicAdd(&s_cnt[part[j]], 1u)) : 0xffffffffu;
+      nk += __popc(okm);
+      __syncthreads();
+      {
+        // one reservation per non-empty partition; all atomics of a thread are in flight together
+        uint32_t basev[QMAX];
+#pragma unroll
+        for (int u = 0; u < QMAX; ++u) {
+          const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
+          basev[u] = 0;
+          if (u < nq && q < pa.n_parts) {
+            const uint32_t cnt = s_cnt[q];
+            if (cnt) basev[u] = atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cnt);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < QMAX; ++u) {
+          const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
+          if (u < nq && q < pa.n_parts) s_cnt[q] = basev[u];
         }
       }
+      __syncthreads();
+      uint32_t base[KPT];
 #pragma unroll
-      for (int u = 0; u < QMAX; ++u) {
-        const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
-        if (u < nq && q < pa.n_parts) s_cnt[q] = basev[u];
-      }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (uint32_t p0 = (uint32_t)tid; p0 < n_owned_syms; p0 += SB * CT_THREADS) {
-      uint32_t info[SB], base[SB];
-      uint64_t can[SB];
+      for (int j = 0; j < KPT; ++j) base[j] = ((okm >> j) & 1u) ? s_cnt[info[j] >> 12] : 0u;
 #pragma unroll
-      for (int u = 0; u < SB; ++u) {
-        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
-        info[u] = p < n_owned_syms ? s_info[p] : 0xffffffffu;
-      }
-#pragma unroll
-      for (int u = 0; u < SB; ++u) {
-        const uint32_t p = p0 + (uint32_t)u * CT_THREADS;
-        const bool ok = info[u] != 0xffffffffu;
-        base[u] = ok ? s_cnt[info[u] >> 12] : 0u;
-        kmer_at(min(p, n_owned_syms - 1u), can[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < SB; ++u) {
-        if (info[u] != 0xffffffffu) {
-          const uint32_t part = info[u] >> 12;
-          const uint32_t pos = base[u] + (info[u] & 0xfffu);
-          if (pos < pa.region_cap) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + (size_t)(part * PART_REPL + repl) * pa.region_cap + pos), can[u]);
-          else probe1<OP>(can[u], T, inserted);
+      for (int j = 0; j < KPT; ++j) {
+        if ((okm >> j) & 1u) {
+          const uint32_t pt = info[j] >> 12;
+          const uint32_t pos = base[j] + (info[j] & 0xfffu);
+          if (pos < pa.region_cap) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + (size_t)(pt * PART_REPL + repl) * pa.region_cap + pos), can[j]);
+          else probe1<OP>(can[j], T, inserted);
         }
       }
     }
