@@ -441,6 +441,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(FinalizeArgs a) {
 // -------------------------------------------------------------------------------------------------
 // launch helpers: tile configuration by number of selected paths
 // -------------------------------------------------------------------------------------------------
+#ifndef PG_SKELETON_CLUSTER_DEFAULT
+#define PG_SKELETON_CLUSTER_DEFAULT 0
+#endif
+
 struct TileCfg {
   int id, L, CPL, RPW, nwarps, nthreads;
 };
@@ -490,6 +494,46 @@ static cudaError_t launch_pair(const ChainParams& p, uint32_t n_chrom, int grid_
     }
   }
   return cudaGetLastError();
+}
+
+// checkpoint walk split over a cluster of C CTAs (hmm_kernels.cuh): NT threads serve ceil(P / C) rows
+template <int L, int CPL, int NT>
+static cudaError_t launch_cluster(const ChainParams& p, uint32_t n_chrom, int C, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_chrom * (uint32_t)C, 2, 1);
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = sizeof(ChainSmem);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, skeleton_cluster_kernel<L, CPL, 1, NT>, p);
+}
+
+// Cluster size of the checkpoint walk: PG_SKELETON_CLUSTER = 0 (single CTA), 2 or 4.  Returns true if the walk was
+// launched on a cluster (configurations with one row per thread, 20 < P <= 68).
+static bool try_cluster_skeleton(const ChainParams& p, uint32_t n_chrom, int cfg_id, cudaStream_t s, cudaError_t& err) {
+  const char* e = getenv("PG_SKELETON_CLUSTER");
+  const int C = e ? atoi(e) : PG_SKELETON_CLUSTER_DEFAULT;
+  if (C != 2 && C != 4) return false;
+  const int rows = ((int)p.P + C - 1) / C, nw = (rows + 7) / 8;   // L = 4: 8 rows per warp
+  if (cfg_id == 3) {                                              // {4, 9, 1}: P <= 36
+    if (nw <= 2) err = launch_cluster<4, 9, 64>(p, n_chrom, C, s);
+    else if (nw == 3) err = launch_cluster<4, 9, 96>(p, n_chrom, C, s);
+    else return false;
+    return true;
+  }
+  if (cfg_id == 4) {                                              // {4, 17, 1}: P <= 68
+    if (nw <= 3) err = launch_cluster<4, 17, 96>(p, n_chrom, C, s);
+    else if (nw <= 5) err = launch_cluster<4, 17, 160>(p, n_chrom, C, s);
+    else return false;
+    return true;
+  }
+  return false;
 }
 
 template <int L, int CPL, int RPW, int NT>
@@ -1039,7 +1083,8 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
       scan_used = 1;
     }
     if (need_skel) {
-      PG_DISPATCH(true, false)
+      le = cudaSuccess;
+      if (!try_cluster_skeleton(cp, e->n_chrom, cfg.id, s, le)) { PG_DISPATCH(true, false) }
       if (le != cudaSuccess) return fail(PG_ERR_CUDA, std::string("skeleton_kernel launch: ") + cudaGetErrorString(le));
       count_launch();
     }

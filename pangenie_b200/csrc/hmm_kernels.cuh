@@ -23,6 +23,8 @@
 //            forward (storing F_t: 8 P^2 bytes per column), then backward fusing the posterior (reading F_t
 //            back).  All SMs busy: this is the HBM-bound kernel the roofline is reported for.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace pg {
@@ -117,13 +119,23 @@ struct Chain {
   double rrow[RPW];
   int w, lane, lr, lc, col0;
   int P;
+  int row0, row_lim;           // rows [row0, row_lim) of the state are this CTA's (the whole matrix unless the chain is split over a cluster)
+  int n_peers;                 // other CTAs of the cluster that need my row sums
+  double* rs_peer[3];          // their rs[][] arrays (distributed shared memory)
   uint32_t vmask;  // bit s set <=> column col0+s < P
   ChainSmem* sm;
   const ChainParams* prm;
   double* post_col;
   const uint16_t* ids_col;
 
-  __device__ __forceinline__ int row(int r) const { return (w * RPW + r) * G + lr; }
+  __device__ __forceinline__ int row(int r) const { return row0 + (w * RPW + r) * G + lr; }
+  // a row sum goes into my rs[buf] and, when the chain is split over a cluster, into every peer's (DSMEM stores)
+  __device__ __forceinline__ void put_rowsum(int buf, int i, double v) const {
+    sm->rs[buf][i] = v;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < n_peers) rs_peer[q][buf * HMM_RS_PAD + i] = v;
+  }
 
   __device__ __forceinline__ void init(ChainSmem* s, const ChainParams* p) {
     sm = s;
@@ -139,6 +151,9 @@ struct Chain {
     vmask = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
     post_col = nullptr;
     ids_col = nullptr;
+    row0 = 0;
+    row_lim = P;
+    n_peers = 0;
   }
 
   __device__ __forceinline__ void sync() const {
@@ -194,7 +209,7 @@ struct Chain {
   __device__ __forceinline__ void store_state(double* dst) const {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      if (row(r) < P) {
+      if (row(r) < row_lim) {
 #pragma unroll
         for (int s = 0; s < CPL; ++s)
           if ((vmask >> s) & 1u) dst[(size_t)(r * CPL + s) * NT + threadIdx.x] = x[r][s];
@@ -204,7 +219,7 @@ struct Chain {
   __device__ __forceinline__ void load_state(const double* src) {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      const bool rok = row(r) < P;
+      const bool rok = row(r) < row_lim;
 #pragma unroll
       for (int s = 0; s < CPL; ++s) x[r][s] = (rok && ((vmask >> s) & 1u)) ? src[(size_t)(r * CPL + s) * NT + threadIdx.x] : 0.0;
     }
@@ -214,7 +229,7 @@ struct Chain {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int i = row(r);
-      if (i < P) {
+      if (i < row_lim) {
 #pragma unroll
         for (int s = 0; s < CPL; ++s)
           if ((vmask >> s) & 1u) dst[(size_t)i * P + col0 + s] = x[r][s];
@@ -225,7 +240,7 @@ struct Chain {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int i = row(r);
-      const bool rok = i < P;
+      const bool rok = i < row_lim;
 #pragma unroll
       for (int s = 0; s < CPL; ++s) x[r][s] = (rok && ((vmask >> s) & 1u)) ? src[(size_t)i * P + col0 + s] : 0.0;
     }
@@ -235,7 +250,7 @@ struct Chain {
     const double uni = 1.0 / ((double)P * (double)P);
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      const bool rok = row(r) < P;
+      const bool rok = row(r) < row_lim;
 #pragma unroll
       for (int s = 0; s < CPL; ++s) {
         const bool ok = rok && ((vmask >> s) & 1u);
@@ -252,7 +267,7 @@ struct Chain {
       for (int s = 0; s < CPL; ++s) acc += x[r][s];
       acc = row_reduce(acc);
       rrow[r] = acc;
-      if (lc == 0 && row(r) < P) sm->rs[buf][row(r)] = acc;
+      if (lc == 0 && row(r) < row_lim) put_rowsum(buf, row(r), acc);
     }
   }
 
@@ -302,7 +317,7 @@ struct Chain {
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
         const int i = row(r);
-        const bool rok = i < P;
+        const bool rok = i < row_lim;
         const uint32_t ib = rok ? (uint32_t)((bw[i >> 6] >> (i & 63)) & 1ull) : 0u;
         const double er0 = rok ? (ib ? e10 : e00) : 0.0, er1 = rok ? (ib ? e11 : e01) : 0.0;
         const double rho = FIRST ? 1.0 : cb * rrow[r] + cc;
@@ -326,7 +341,7 @@ struct Chain {
         acc += acc2;
         acc = row_reduce(acc);
         rrow[r] = acc;
-        if (lc == 0 && rok) sm->rs[nbuf][i] = acc;
+        if (lc == 0 && rok) put_rowsum(nbuf, i, acc);
         if (WITH_POST) {
           w0 = row_reduce(w0);
           w1 = row_reduce(w1);
@@ -350,7 +365,7 @@ struct Chain {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int i = row(r);
-      const bool rok = i < P;
+      const bool rok = i < row_lim;
       const uint32_t ai = rok ? aidx[i] : 0;
       const double rho = FIRST ? 1.0 : cb * rrow[r] + cc;
       double acc = 0.0;
@@ -379,7 +394,7 @@ struct Chain {
       }
       acc = row_reduce(acc);
       rrow[r] = acc;
-      if (lc == 0 && rok) sm->rs[nbuf][i] = acc;
+      if (lc == 0 && rok) put_rowsum(nbuf, i, acc);
       if (WITH_POST && fastA) {
 #pragma unroll
         for (int q = 0; q < HMM_FAST_A; ++q) {
@@ -521,6 +536,116 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
     }
   }
   cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// phase 1 over a thread-block CLUSTER.  The walk above is bound by what one SM can issue and move per column (ncu at
+// P = 65: 2300 cycles per column with 9 warps, issue + shared-memory pipes; shortening or re-ordering the dependent chain
+// did not move it), and the longest chromosome's walk is the critical path of the whole stage once the sample is sharded
+// over GPUs.  Here the ROWS of the state are split over the CTAs of a cluster (2 or 4 SMs per chain): every CTA computes
+// the cells of its rows for all P columns, writes the row sums it produces into its own shared memory AND into its peers'
+// (distributed shared memory), and one cluster barrier per column (arrive.release / wait.acquire) replaces the CTA
+// barrier.  Everything else - descriptors, scaling, the uniform replacement of dead columns, the dense checkpoints (rows
+// are disjoint) - is the code of the single-CTA walk; the results are bitwise the same because every cell is computed by
+// the same expression from the same row sums (the total is summed in the same order by every warp).
+// grid = (n_chrom * C, 2), cluster = (C, 1, 1); NT threads serve ceil(P / C) rows.
+// -------------------------------------------------------------------------------------------------
+template <int L, int CPL, int RPW, int NT>
+__global__ void __launch_bounds__(NT) skeleton_cluster_kernel(const ChainParams p) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  Chain<L, CPL, RPW, NT> ch;
+  ch.init(sm, &p);
+  const int rows_per = ((int)p.P + C - 1) / C;
+  ch.row0 = rank * rows_per;
+  ch.row_lim = min((int)p.P, ch.row0 + rows_per);
+  ch.n_peers = C - 1;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) ch.rs_peer[q] = cluster.map_shared_rank(&sm->rs[0][0], (rank + 1 + q) % C);   // (entries >= n_peers unused)
+  const ChromCols cc = p.chroms[blockIdx.x / C];
+  if (cc.n_blocks <= 1) return;                               // (the whole cluster takes the same branch)
+  if (p.seq_flags && !p.seq_flags[blockIdx.x / C]) return;
+  for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;  // zero padding beyond P
+  cluster.sync();                                             // nobody writes into a peer's rs[] before it is zeroed
+  const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
+  const size_t CS = p.ckpt_stride;
+  double nou[RPW][CPL];
+  constexpr int D = HMM_PREFETCH;
+  int cur = 0;
+  if (blockIdx.y == 0) {
+    const int last = c0 + (int)(cc.n_blocks - 1) * B - 1;
+    int slot = ch.slot_of(c0), pslot = slot;
+    for (int d = 0; d < D; ++d) {
+      ch.prefetch_desc(c0 + d, c0, c1, pslot);
+      pslot = ch.slot_next(pslot);
+    }
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    ch.template step<false, true, false>(slot, 0, 0, 0.0, nou, 0);
+    ch.prefetch_desc(c0 + D, c0, c1, pslot);
+    pslot = ch.slot_next(pslot);
+    cp_async_wait<D - 1>();
+    cluster.sync();
+    slot = ch.slot_next(slot);
+    int until_ckpt = B - 1;
+    uint32_t blk = cc.blk_begin + 1;
+    for (int t = c0 + 1; t <= last; ++t) {
+      if (until_ckpt == 0) {
+        ch.store_dense(p.ckpt_fwd + (size_t)blk * CS);
+        ++blk;
+        until_ckpt = B;
+      }
+      --until_ckpt;
+      const double T = ch.total(cur);
+      ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nou, 0);
+      ch.prefetch_desc(t + D, c0, c1, pslot);
+      pslot = ch.slot_next(pslot);
+      cp_async_wait<D - 1>();
+      cluster.sync();
+      slot = ch.slot_next(slot);
+      cur ^= 1;
+    }
+    ch.store_dense(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * CS);
+  } else {
+    const int first = c0 + B;
+    int slot = ch.slot_of(c1 - 1), pslot = slot;
+    for (int d = 0; d < D; ++d) {
+      ch.prefetch_desc(c1 - 1 - d, c0, c1, pslot);
+      pslot = ch.slot_prev(pslot);
+    }
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    ch.template step<true, true, false>(slot, 0, 0, 0.0, nou, 0);
+    int rel = (c1 - 1 - c0) % B;
+    uint32_t blk = cc.blk_begin + (uint32_t)((c1 - 1 - c0) / B);
+    if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
+    ch.prefetch_desc(c1 - 1 - D, c0, c1, pslot);
+    pslot = ch.slot_prev(pslot);
+    cp_async_wait<D - 1>();
+    cluster.sync();
+    slot = ch.slot_prev(slot);
+    for (int t = c1 - 2; t >= first; --t) {
+      if (rel == 0) {
+        rel = B;
+        --blk;
+      }
+      --rel;
+      const double T = ch.total(cur);
+      ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nou, 0);
+      if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
+      ch.prefetch_desc(t - D, c0, c1, pslot);
+      pslot = ch.slot_prev(pslot);
+      cp_async_wait<D - 1>();
+      cluster.sync();
+      slot = ch.slot_prev(slot);
+      cur ^= 1;
+    }
+  }
+  cp_async_wait<0>();
+  cluster.sync();  // no CTA leaves while a peer may still write into its shared memory
 }
 
 // -------------------------------------------------------------------------------------------------

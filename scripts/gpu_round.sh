@@ -66,10 +66,15 @@ u=d["roofline"]["update_pass"]
 print("direct (no partitioning): step_ms", round(d["ms_per_step"],1), "update_ms", round(u["ms"],1))
 EOF
   ;;
-hmm_lean)
-  for lean in 0 1; do
-    PG_SKELETON_LEAN=$lean timeout 900 python scripts/bench_hmm.py --haplotypes 32 64 --variants 400000 --repeat 2 > $out/bench_hmm_lean${lean}_$tag.jsonl 2> $out/bench_hmm_lean${lean}_$tag.err
-    cat $out/bench_hmm_lean${lean}_$tag.jsonl; tail -2 $out/bench_hmm_lean${lean}_$tag.err
+hmm_cluster)
+  for c in 0 2 4; do
+    PG_SKELETON_CLUSTER=$c timeout 900 python scripts/bench_hmm.py --haplotypes 32 64 --variants 400000 --repeat 2 > $out/bench_hmm_cluster${c}_$tag.jsonl 2> $out/bench_hmm_cluster${c}_$tag.err
+    python - <<EOF
+import json
+for l in open("$out/bench_hmm_cluster${c}_$tag.jsonl"):
+    d=json.loads(l); print("cluster", $c, "H", d["haplotypes"], "skeleton_ms", round(d["skeleton_ms"],2), "blocks_ms", round(d["blocks_ms"],2))
+EOF
+    tail -2 $out/bench_hmm_cluster${c}_$tag.err
   done;;
 ncu_hmm)
   PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"skeleton_kernel|block_kernel" -s 1 -c 2 -o $out/prof_hmm_$tag \

@@ -258,3 +258,36 @@ def test_path_counts_at_kernel_configuration_boundaries(engine, oracle, n_paths)
         want = oracles.cpu_hmm_run(oracle, "pgo_", [panel], table, **kw)[0]
         got = engine.hmm_run([panel], table, **kw)[0]
         assert_results_close(got, want, atol=1e-300, label=f"P={n_paths} normalize={normalize}")
+
+
+@pytest.mark.parametrize("n_paths", [21, 33, 36, 37, 65, 68])
+def test_cluster_checkpoint_walk_is_bitwise_identical(engine, oracle, monkeypatch, n_paths):
+    """The checkpoint walk split over a thread-block cluster (rows over 2 or 4 CTAs, row sums exchanged through distributed
+    shared memory, one cluster barrier per column) computes every cell by the same expression from the same row sums as
+    the single-CTA walk: identical bits; multi-allelic columns and columns whose total underflows included."""
+    rng = np.random.default_rng(800 + n_paths)
+    panel = random_panel(rng, 700, n_paths, max_alleles=3, undefined_frac=0.05, ref_only_frac=0.02, kmers_per_allele=(0, 8))
+    probs = pg.ProbabilityTable(0, 1, 21, 0.0)   # exact zeros: some column totals are exactly zero (uniform replacement)
+    probs.modify_probability(0, 10, 0.0, 1.0, 0.0)
+    probs.modify_probability(0, 20, 0.0, 0.0, 1.0)
+    probs.modify_probability(0, 0, 1.0, 0.0, 0.0)
+    b = pg.PanelBuilder()
+    pos = 1000
+    for i in range(400):
+        pos += int(rng.integers(100, 2000))
+        al = rng.integers(0, 2, size=n_paths)
+        al[0], al[1] = 0, 1
+        v = b.add_variant(pos, al)
+        c = [(10, 10), (20, 0), (0, 20), (10, 0)][int(rng.integers(0, 4))]
+        b.insert_kmer(v, c[0], [0]); b.insert_kmer(v, c[1], [1])
+    dead = b.build()
+    for p, t, kw in ((panel, _table(), dict(recombrate=1.26, effective_N=1e-5)), (dead, probs, dict(recombrate=1.26, effective_N=25000.0))):
+        monkeypatch.setenv("PG_SKELETON_CLUSTER", "0")
+        one = engine.hmm_run([p, p], t, **kw)
+        want = oracles.cpu_hmm_run(oracle, "pgo_", [p], t, **kw)[0]
+        assert_results_close(one[0], want, atol=1e-300, label=f"single CTA P={n_paths}")
+        for C in ("2", "4"):
+            monkeypatch.setenv("PG_SKELETON_CLUSTER", C)
+            got = engine.hmm_run([p, p], t, **kw)
+            for g, o in zip(got, one):
+                assert np.array_equal(g.likelihoods, o.likelihoods) and np.array_equal(g.genotype, o.genotype), (n_paths, C)
