@@ -526,8 +526,9 @@ __device__ __forceinline__ uint32_t part_of(uint64_t kmer, uint32_t n_parts) {
   return __umulhi((uint32_t)(hash_kmer(kmer) >> 32), n_parts);  // monotone in the home bucket index (home_slot)
 }
 
-constexpr size_t SCATTER_SMEM_MAX = (size_t)(MAX_PARTS + 1) * 4;  // s_cnt at the largest partition count
-static inline size_t scatter_smem(uint32_t n_parts) { return (size_t)(n_parts + 1) * 4; }
+constexpr int SCATTER_SUB = 8 * CT_THREADS;  // start positions per sub-round of the scatter pass (KPT per thread)
+constexpr size_t SCATTER_SMEM_MAX = (size_t)SCATTER_SUB * 12 + (size_t)(MAX_PARTS + 1) * 8;  // staging + s_cnt + s_loc at the largest partition count
+static inline size_t scatter_smem(uint32_t n_parts) { return (size_t)SCATTER_SUB * 12 + (size_t)(n_parts + 1) * 8; }
 constexpr int PK_WORDS = CT_TILE / 16 + 4;  // packed codes: 16 symbols per word (+ read-ahead padding)
 constexpr int NB_WORDS = CT_TILE / 32 + 4;  // not-a-base flags: 32 symbols per word
 
@@ -546,7 +547,10 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
   // scatter mode (dynamic shared memory): the per-partition counts of the tile -> write cursors; each k-mer costs ONE
   // shared-memory atomic (it returns the rank within the partition)
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_dyn);                                            // [n_parts]
+  unsigned long long* s_stage = reinterpret_cast<unsigned long long*>(s_dyn);                      // [SCATTER_SUB] staged k-mers
+  uint32_t* s_dst = reinterpret_cast<uint32_t*>(s_stage + SCATTER_SUB);                            // [SCATTER_SUB] their destinations
+  uint32_t* s_cnt = s_dst + SCATTER_SUB;                                                           // [n_parts] counts, then write cursors
+  uint32_t* s_loc = s_cnt + pa.n_parts;                                                            // [n_parts] offsets in the staging array
   unsigned long long* scalars = T.scalars;
   if (SCATTER)
     for (uint32_t i = threadIdx.x; i < pa.n_parts; i += CT_THREADS) s_cnt[i] = 0;
@@ -716,7 +720,7 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
     // (1) rank my k-mers within their partition (the shared-memory atomic returns the rank), (2) reserve one contiguous
     // range per partition in this tile's replica region, (3) append.  A region that is full (skewed data) sends its
     // k-mers straight to the table.  A FASTQ tile (about half of its bytes are sequence) is one sub-round.
-    constexpr int KPT = 8;
+    constexpr int KPT = SCATTER_SUB / CT_THREADS;
     const uint32_t repl = blockIdx.x % PART_REPL;
     const int nq = (int)((pa.n_parts + CT_THREADS - 1) / CT_THREADS);
     constexpr int QMAX = (MAX_PARTS + CT_THREADS) / CT_THREADS;
@@ -761,19 +765,28 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
       for (int j = 0; j < KPT; ++j) part[j] = part_of(can[j], pa.n_parts);
 #pragma unroll
       for (int j = 0; j < KPT; ++j) info[j] = ((okm >> j) & 1u) ? ((part[j] << 12) | atomicAdd(&s_cnt[part[j]], 1u)) : 0xffffffffu;
+      if (T.flags & 16u) okm = 0;
       nk += __popc(okm);
       __syncthreads();
+      uint32_t n_staged;
       {
-        // one reservation per non-empty partition; all atomics of a thread are in flight together
-        uint32_t basev[QMAX];
+        // per partition: offset of its k-mers in the tile's staging array (exclusive scan of the counts) and one
+        // reservation in the replica region (all atomics of a thread in flight together)
+        uint32_t cntv[QMAX], basev[QMAX], mine = 0;
+#pragma unroll
+        for (int u = 0; u < QMAX; ++u) {
+          const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
+          cntv[u] = (u < nq && q < pa.n_parts) ? s_cnt[q] : 0u;
+          mine += cntv[u];
+        }
+        uint32_t run = block_exscan_add(mine, s_warp, &n_staged);
 #pragma unroll
         for (int u = 0; u < QMAX; ++u) {
           const uint32_t q = (uint32_t)tid + (uint32_t)u * CT_THREADS;
           basev[u] = 0;
-          if (u < nq && q < pa.n_parts) {
-            const uint32_t cnt = s_cnt[q];
-            if (cnt) basev[u] = atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cnt);
-          }
+          if (cntv[u]) basev[u] = atomicAdd(pa.cursor + (size_t)(q * PART_REPL + repl) * CURSOR_STRIDE, cntv[u]);
+          if (u < nq && q < pa.n_parts) s_loc[q] = run;
+          run += cntv[u];
         }
 #pragma unroll
         for (int u = 0; u < QMAX; ++u) {
@@ -782,17 +795,27 @@ count_tile_kernel(const char* __restrict__ text, uint64_t n, uint64_t n_avail, i
         }
       }
       __syncthreads();
-      uint32_t base[KPT];
-#pragma unroll
-      for (int j = 0; j < KPT; ++j) base[j] = ((okm >> j) & 1u) ? s_cnt[info[j] >> 12] : 0u;
+      // stage: the k-mers of a partition become neighbours in shared memory, each with its destination element
 #pragma unroll
       for (int j = 0; j < KPT; ++j) {
         if ((okm >> j) & 1u) {
-          const uint32_t pt = info[j] >> 12;
-          const uint32_t pos = base[j] + (info[j] & 0xfffu);
-          if (pos < pa.region_cap) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + (size_t)(pt * PART_REPL + repl) * pa.region_cap + pos), can[j]);
-          else probe1<OP>(can[j], T, inserted);
+          const uint32_t pt = info[j] >> 12, rk = info[j] & 0xfffu;
+          const uint32_t i = s_loc[pt] + rk, pos = s_cnt[pt] + rk;
+          if (pos < pa.region_cap) {
+            s_stage[i] = can[j];
+            s_dst[i] = (pt * PART_REPL + repl) * pa.region_cap + pos;   // < 2^32 elements (part_setup)
+          } else {
+            s_dst[i] = 0xffffffffu;
+            probe1<OP>(can[j], T, inserted);
+          }
         }
+      }
+      __syncthreads();
+      // append: consecutive threads write consecutive staged k-mers = runs of consecutive addresses per partition (scattered
+      // 8-byte stores straight from the registers were 48% of this kernel's time: 32 sectors per warp store)
+      for (uint32_t i = (uint32_t)tid; i < n_staged; i += CT_THREADS) {
+        const uint32_t d = s_dst[i];
+        if (d != 0xffffffffu) __stcs(reinterpret_cast<unsigned long long*>(pa.buf + d), s_stage[i]);
       }
     }
   }
@@ -1047,7 +1070,7 @@ static TableRef table_ref(const pg_counter* c) {
   T.cap_q = c->cap_q;
   T.cap_sh = c->cap_sh;
   T.scalars = c->d_scalars;
-  T.flags = env_u64("PG_COUNT_NOAGG", 0) ? 1u : 0u;
+  T.flags = (env_u64("PG_COUNT_NOAGG", 0) ? 1u : 0u) | ((uint32_t)env_u64("PG_COUNT_DEBUG", 0) & 0xf0u);   // DEBUG: timing dissection only
   return T;
 }
 
@@ -1122,6 +1145,7 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is
     kcap = std::min<uint64_t>(kcap, std::max<uint64_t>(budget / 8, c->part_buf_cap));
     kcap = std::max<uint64_t>(kcap, n_regions * 8192);
   }
+  kcap = std::min<uint64_t>(kcap, 0xfff00000ull);   // destinations are 32-bit element indices in the scatter kernel
   const uint64_t region = std::min<uint64_t>((kcap / n_regions) & ~(uint64_t)15, 0xfffffff0ull);
   const uint64_t need = region * n_regions;
   if (c->part_buf_cap < need) {
