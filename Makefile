@@ -4,7 +4,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xptxas -v
 CSRC := pangenie_b200/csrc
 LIB := pangenie_b200/libpangenie_b200.so
-SRCS := $(CSRC)/host_model.cu $(CSRC)/kmer_count.cu $(CSRC)/genotype.cu $(CSRC)/index_io.cu $(CSRC)/sampler.cu
+SRCS := $(CSRC)/host_model.cu $(CSRC)/kmer_count.cu $(CSRC)/genotype.cu $(CSRC)/index_io.cu $(CSRC)/sampler.cu $(CSRC)/index_build.cu
 HDRS := $(CSRC)/common.cuh $(CSRC)/hmm_kernels.cuh $(CSRC)/hmm_scan.cuh include/pangenie_b200.h
 
 .PHONY: all lib oracle ref tools clean

@@ -343,6 +343,59 @@ int pg_haplotype_sample(int device, const pg_panel* panel, uint32_t size, double
 /** Empties a counter (all keys removed, counts zero) so its HBM allocation can be reused. */
 int pg_count_clear(pg_counter* c);
 
+/* ------------------------------------------------------------------------------------------------
+ * Index stage: unique-k-mer selection, `StepwiseUniqueKmerComputer::compute_unique_kmers`
+ * (src/stepwiseuniquekmercomputer.cpp:95-197) with `select_kmers` (:46-93), `stepwise_unique_kmers` (:11-34) and
+ * `determine_unique_flanking_kmers` (:227-264), run by `PanGenie-index` once per chromosome (src/commands.cpp:647-700)
+ * against the k-mer counts of `<prefix>_path_segments.fasta` (COUNT mode: `pg_count_create(segments, NULL, ...)`).
+ *
+ * Input = what the computer reads from the reference's `Graph` for ONE chromosome, flattened (all arrays host memory,
+ * caller-owned): per variant bubble v its alleles 0..n_v-1 (`allele_offsets`), per allele `Variant::get_allele_sequence(a)`
+ * (flanks of k-1 bases included, ASCII, any character outside ACGT is an undefined base) and
+ * `Variant::is_undefined_allele(a)`, per path `Variant::get_allele_on_path(p)`, and `Graph::get_left_overhang(v, 2k)` /
+ * `get_right_overhang(v, 2k)` (src/graph.cpp:554-592).
+ *
+ * Result = the chromosome's `std::vector<std::shared_ptr<UniqueKmers>>` as a `pg_panel` (coverage and counts zero, as the
+ * index stage leaves them; `kmer_codes` / `flank_codes` = the k-mers of `<prefix>_<chrom>_kmers.tsv.gz` as they occur on the
+ * allele, i.e. NOT canonicalised, 2-bit packed with the first base most significant), owned by the handle.
+ * Per variant: every k-mer of a defined allele that occurs exactly once in that allele, on exactly one allele of the bubble
+ * and nowhere else in the graph, and whose allele is carried by a path, in ascending k-mer order per allele; alleles take
+ * turns (ascending allele id) until every allele has 16 (all paths on alleles 0/1) or 32 k-mers or max(301, P) k-mers are
+ * selected; k-mer i of the variant is the i-th in (allele id, k-mer) order.  Flanks: up to 12 k-mers per side, ascending, that
+ * occur once in the overhang and once in the graph.  One CTA per variant: enumeration, a bitonic sort in shared memory (global
+ * scratch for bubbles with more than 2048 k-mers), probes of the graph table, selection.  Integer work: identical to the
+ * reference.  Limits: k <= 32, at most 65535 alleles per bubble.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t n_variants;              /* V */
+  uint32_t n_paths;                 /* P */
+  uint32_t k;
+  const uint64_t* positions;        /* [V]   Variant::get_start_position()                       */
+  const uint64_t* end_positions;    /* [V]   Variant::get_end_position(); only written to the tsv; may be NULL */
+  const uint16_t* path_to_allele;   /* [V*P] Variant::get_allele_on_path(p)                      */
+  const uint32_t* allele_offsets;   /* [V+1] CSR over the alleles of each bubble                 */
+  const uint8_t* allele_undefined;  /* [A]   Variant::is_undefined_allele(a)                     */
+  const uint64_t* seq_offsets;      /* [A+1] CSR over `seq`                                      */
+  const char* seq;                  /*       Variant::get_allele_sequence(a), concatenated      */
+  const uint64_t* left_offsets;     /* [V+1] CSR over `left_seq`                                 */
+  const char* left_seq;             /*       Graph::get_left_overhang(v, 2k)                    */
+  const uint64_t* right_offsets;    /* [V+1] */
+  const char* right_seq;            /*       Graph::get_right_overhang(v, 2k)                   */
+} pg_variants;
+
+typedef struct pg_unique_kmers pg_unique_kmers;
+/** NULL on error (pg_last_error()).  `graph_counts` must hold the COUNT of the path-segment file. */
+pg_unique_kmers* pg_unique_kmers_compute(int device, const pg_counter* graph_counts, const pg_variants* in);
+/** The panel of the chromosome; arrays stay valid until pg_unique_kmers_free. */
+int pg_unique_kmers_panel(pg_unique_kmers* u, pg_panel* out);
+/** Device time of the selection kernel (ms) and the k-mers it enumerated. */
+int pg_unique_kmers_stats(const pg_unique_kmers* u, double* kernel_ms, uint64_t* kmers_enumerated);
+/** Writes `<prefix>_<chrom>_kmers.tsv.gz` (src/stepwiseuniquekmercomputer.cpp:104-105, 151-182; read back by
+ *  src/kmerparser.cpp:16-28): header + one line per variant `chrom start end k-mers flank-k-mers`, "nan" for none. */
+int pg_unique_kmers_write_tsv(const pg_unique_kmers* u, const char* chromosome, const uint64_t* end_positions,
+                              const char* path);
+void pg_unique_kmers_free(pg_unique_kmers* u);
+
 /* ---- measurement hooks (bench.py): per-stage device times of the last call on this engine ---- */
 typedef struct {
   double count_ms, histogram_ms, fill_ms, emission_ms, hmm_skeleton_ms, hmm_blocks_ms, finalize_ms;

@@ -65,6 +65,13 @@ int pgo_haplotype_sample(const pg_panel* panel, uint32_t size, double recombrate
                          uint16_t allele_penalty, uint64_t* sampled_paths, uint32_t* best_scores,
                          uint16_t* new_path_to_allele, uint32_t* new_kmer_count, uint16_t* new_counts);
 
+/* ---- index stage: unique-k-mer selection (src/stepwiseuniquekmercomputer.cpp:11-93, 95-197, 227-264); see
+ * pg_oracle_index.cpp.  `graph` = COUNT of the path-segment file. ---- */
+typedef struct pgo_unique_kmers pgo_unique_kmers;
+pgo_unique_kmers* pgo_unique_kmers_compute(const pgo_counter* graph, const pg_variants* in);
+int pgo_unique_kmers_panel(pgo_unique_kmers* u, pg_panel* out);
+void pgo_unique_kmers_free(pgo_unique_kmers* u);
+
 #ifdef __cplusplus
 }
 #endif

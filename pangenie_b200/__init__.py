@@ -4,8 +4,8 @@
 host-side mirror of the reference's interface plus multi-GPU plumbing over torch.distributed.
 """
 from .capi import PG_OP_COUNT, PG_OP_PRIME, PG_OP_UPDATE, load  # noqa: F401
-from .model import HMM, Engine, Index, KmerCounter, PgError, ProbabilityTable, copy_number, haplotype_sample  # noqa: F401
+from .model import HMM, Engine, Index, KmerCounter, PgError, ProbabilityTable, UniqueKmerSelection, copy_number, haplotype_sample  # noqa: F401
 from .panel import Panel, PanelBuilder, Result  # noqa: F401
 
 __all__ = ["HMM", "Engine", "Index", "KmerCounter", "PgError", "ProbabilityTable", "copy_number", "Panel", "PanelBuilder",
-           "Result", "haplotype_sample", "PG_OP_COUNT", "PG_OP_PRIME", "PG_OP_UPDATE", "load"]
+           "Result", "UniqueKmerSelection", "haplotype_sample", "PG_OP_COUNT", "PG_OP_PRIME", "PG_OP_UPDATE", "load"]

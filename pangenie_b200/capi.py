@@ -84,6 +84,25 @@ class PgGenotypeInput(C.Structure):
     ]
 
 
+class PgVariants(C.Structure):
+    _fields_ = [
+        ("n_variants", C.c_uint32),
+        ("n_paths", C.c_uint32),
+        ("k", C.c_uint32),
+        ("positions", C.c_void_p),
+        ("end_positions", C.c_void_p),
+        ("path_to_allele", C.c_void_p),
+        ("allele_offsets", C.c_void_p),
+        ("allele_undefined", C.c_void_p),
+        ("seq_offsets", C.c_void_p),
+        ("seq", C.c_void_p),
+        ("left_offsets", C.c_void_p),
+        ("left_seq", C.c_void_p),
+        ("right_offsets", C.c_void_p),
+        ("right_seq", C.c_void_p),
+    ]
+
+
 class PgTimings(C.Structure):
     _fields_ = [
         ("count_ms", C.c_double),
@@ -119,6 +138,7 @@ EXPORTS = [
     "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted", "pg_hmm_run_subsets",
     "pg_index_open", "pg_index_open_archive", "pg_index_close", "pg_index_kmer_size", "pg_index_n_chromosomes",
     "pg_index_chromosome_name", "pg_index_add_reference", "pg_index_segments_path", "pg_index_panel",
+    "pg_unique_kmers_compute", "pg_unique_kmers_panel", "pg_unique_kmers_stats", "pg_unique_kmers_write_tsv", "pg_unique_kmers_free",
 ]
 
 
@@ -172,6 +192,15 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "count_compute_histogram", i32, [vp, u64, i32, C.c_char_p, C.POINTER(u64)])
         _sig(lib, p + "count_distinct", u64, [vp])
         _sig(lib, p + "count_destroy", None, [vp])
+    if has("unique_kmers_compute"):
+        if p == "pg_":
+            _sig(lib, p + "unique_kmers_compute", vp, [i32, vp, C.POINTER(PgVariants)])
+            _sig(lib, p + "unique_kmers_stats", i32, [vp, C.POINTER(dbl), C.POINTER(u64)])
+            _sig(lib, p + "unique_kmers_write_tsv", i32, [vp, C.c_char_p, vp, C.c_char_p])
+        else:
+            _sig(lib, p + "unique_kmers_compute", vp, [vp, C.POINTER(PgVariants)])
+        _sig(lib, p + "unique_kmers_panel", i32, [vp, C.POINTER(PgPanel)])
+        _sig(lib, p + "unique_kmers_free", None, [vp])
     if has("histogram_peak"):
         _sig(lib, p + "histogram_peak", i32, [vp, u64, i32, C.POINTER(u64)])
     if has("probtable_init"):

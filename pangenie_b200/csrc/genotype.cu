@@ -536,6 +536,38 @@ static bool try_cluster_skeleton(const ChainParams& p, uint32_t n_chrom, int cfg
   return false;
 }
 
+// Checkpoint walk with FEW lanes per row (hmm_kernels.cuh, "row-per-lane"): the walk is bound by the instructions and
+// shared-memory reads one SM spends per column, and both fall with the number of warps a chain is spread over (every lane
+// reads the row sum of each of its columns once per column: lanes that own whole rows share those reads as broadcasts).
+// The dense checkpoints are independent of the tile configuration, so the block kernel keeps its own.
+// PG_SKELETON_TILE = 0 (the block kernel's configuration), 1 (one lane per row) or 2 (two lanes per row).
+template <int L, int CPL, int NT>
+static cudaError_t launch_rowlane(const ChainParams& p, uint32_t n_chrom, cudaStream_t s) {
+  skeleton_kernel<L, CPL, 1, NT><<<dim3(n_chrom, 2), NT, sizeof(ChainSmem), s>>>(p);
+  return cudaGetLastError();
+}
+#ifndef PG_SKELETON_TILE_DEFAULT
+#define PG_SKELETON_TILE_DEFAULT 0
+#endif
+static bool try_rowlane_skeleton(const ChainParams& p, uint32_t n_chrom, cudaStream_t s, cudaError_t& err) {
+  const char* e = getenv("PG_SKELETON_TILE");
+  const int mode = e ? atoi(e) : PG_SKELETON_TILE_DEFAULT;
+  const int P = (int)p.P;
+  if (mode == 1) {
+    if (P > 16 && P <= 33) err = launch_rowlane<1, 33, 64>(p, n_chrom, s);
+    else if (P > 33 && P <= 65) err = launch_rowlane<1, 65, 96>(p, n_chrom, s);
+    else return false;
+    return true;
+  }
+  if (mode == 2) {
+    if (P > 16 && P <= 34) err = launch_rowlane<2, 17, 96>(p, n_chrom, s);
+    else if (P > 34 && P <= 66) err = launch_rowlane<2, 33, 160>(p, n_chrom, s);
+    else return false;
+    return true;
+  }
+  return false;
+}
+
 template <int L, int CPL, int RPW, int NT>
 static int occupancy_of() {
   int n = 0;
@@ -1084,7 +1116,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     }
     if (need_skel) {
       le = cudaSuccess;
-      if (!try_cluster_skeleton(cp, e->n_chrom, cfg.id, s, le)) { PG_DISPATCH(true, false) }
+      if (!try_rowlane_skeleton(cp, e->n_chrom, s, le) && !try_cluster_skeleton(cp, e->n_chrom, cfg.id, s, le)) { PG_DISPATCH(true, false) }
       if (le != cudaSuccess) return fail(PG_ERR_CUDA, std::string("skeleton_kernel launch: ") + cudaGetErrorString(le));
       count_launch();
     }

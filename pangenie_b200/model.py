@@ -382,6 +382,86 @@ class HMM:
         return self.result
 
 
+def panel_from_struct(ps: PgPanel) -> Panel:
+    """numpy COPIES of the library-owned arrays of a pg_panel."""
+    V, P = ps.n_variants, ps.n_paths
+
+    def arr(addr, n, dt):
+        if not addr or n == 0:
+            return np.zeros(0, dt) if addr or n == 0 else None
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+    koff = arr(ps.kmer_offsets, V + 1, np.uint32)
+    aoff = arr(ps.allele_offsets, V + 1, np.uint32)
+    K, A = int(koff[-1]) if V else 0, int(aoff[-1]) if V else 0
+    pan = Panel(P, arr(ps.positions, V, np.uint64), arr(ps.path_to_allele, V * P, np.uint16), arr(ps.coverage, V, np.uint16),
+                koff, arr(ps.kmer_counts, K, np.uint16), aoff, arr(ps.allele_ids, A, np.uint16),
+                arr(ps.allele_undefined, A, np.uint8), arr(ps.allele_kmer_offset, A, np.uint16), arr(ps.allele_kmer_mask, A, np.uint32))
+    if ps.flank_offsets:
+        foff = arr(ps.flank_offsets, V + 1, np.uint32)
+        pan.kmer_codes = arr(ps.kmer_codes, K, np.uint64)
+        pan.flank_offsets = foff
+        pan.flank_codes = arr(ps.flank_codes, int(foff[-1]) if V else 0, np.uint64)
+    return pan
+
+
+def variants_struct(flat: dict):
+    """pg_variants over the flat numpy arrays of one chromosome (keys = the struct's field names); returns
+    (struct, keep-alive list)."""
+    from .capi import PgVariants
+    vs = PgVariants()
+    vs.n_variants, vs.n_paths, vs.k = int(flat["n_variants"]), int(flat["n_paths"]), int(flat["k"])
+    keep = []
+    for name, dt in (("positions", np.uint64), ("end_positions", np.uint64), ("path_to_allele", np.uint16),
+                     ("allele_offsets", np.uint32), ("allele_undefined", np.uint8), ("seq_offsets", np.uint64), ("seq", np.uint8),
+                     ("left_offsets", np.uint64), ("left_seq", np.uint8), ("right_offsets", np.uint64), ("right_seq", np.uint8)):
+        a = flat.get(name)
+        if a is None:
+            continue
+        a = np.ascontiguousarray(a, dt)
+        if a.size == 0:
+            a = np.zeros(1, dt)          # a valid address for empty arrays
+        keep.append(a)
+        setattr(vs, name, a.ctypes.data)
+    return vs, keep
+
+
+class UniqueKmerSelection:
+    """The index stage's unique-k-mer selection for one chromosome on the device (pg_unique_kmers_*; reference
+    src/stepwiseuniquekmercomputer.cpp:95-197).  `graph_counts` is a Counter holding the COUNT of the path segments."""
+
+    def __init__(self, graph_counts: "KmerCounter", flat: dict, device: int = 0):
+        self._lib = capi.load()
+        vs, keep = variants_struct(flat)
+        self._h = self._lib.pg_unique_kmers_compute(device, graph_counts._h, C.byref(vs))
+        if not self._h:
+            raise PgError(-1, self._lib.pg_last_error().decode())
+
+    def panel(self) -> Panel:
+        ps = PgPanel()
+        _check(self._lib, self._lib.pg_unique_kmers_panel(self._h, C.byref(ps)))
+        return panel_from_struct(ps)
+
+    def stats(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(self._lib, self._lib.pg_unique_kmers_stats(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def write_tsv(self, chromosome: str, end_positions, path: str):
+        ends = np.ascontiguousarray(end_positions, np.uint64)
+        _check(self._lib, self._lib.pg_unique_kmers_write_tsv(self._h, chromosome.encode(), ends.ctypes.data, os.fsencode(path)))
+
+    def close(self):
+        if self._h:
+            self._lib.pg_unique_kmers_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Index:
     """The index artefacts of `PanGenie-index` read by the native reader (csrc/index_io.cu, pg_index_*): what
     `PanGenie -f <prefix>` loads before the hot path starts (reference src/commands.cpp:760-790, 98-137)."""
@@ -415,24 +495,7 @@ class Index:
         """Chromosome i as a Panel (numpy COPIES of the index-owned arrays)."""
         ps = PgPanel()
         _check(self._lib, self._lib.pg_index_panel(self._h, i, C.byref(ps)))
-        V, P = ps.n_variants, ps.n_paths
-
-        def arr(addr, n, dt):
-            if not addr or n == 0:
-                return np.zeros(0, dt) if addr or n == 0 else None
-            return np.ctypeslib.as_array(C.cast(addr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
-        koff = arr(ps.kmer_offsets, V + 1, np.uint32)
-        aoff = arr(ps.allele_offsets, V + 1, np.uint32)
-        K, A = int(koff[-1]) if V else 0, int(aoff[-1]) if V else 0
-        pan = Panel(P, arr(ps.positions, V, np.uint64), arr(ps.path_to_allele, V * P, np.uint16), arr(ps.coverage, V, np.uint16),
-                    koff, arr(ps.kmer_counts, K, np.uint16), aoff, arr(ps.allele_ids, A, np.uint16),
-                    arr(ps.allele_undefined, A, np.uint8), arr(ps.allele_kmer_offset, A, np.uint16), arr(ps.allele_kmer_mask, A, np.uint32))
-        if ps.flank_offsets:
-            foff = arr(ps.flank_offsets, V + 1, np.uint32)
-            pan.kmer_codes = arr(ps.kmer_codes, K, np.uint64)
-            pan.flank_offsets = foff
-            pan.flank_codes = arr(ps.flank_codes, int(foff[-1]) if V else 0, np.uint64)
-        return pan
+        return panel_from_struct(ps)
 
     def close(self):
         if self._h:

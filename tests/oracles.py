@@ -171,3 +171,18 @@ def cpu_haplotype_sample(lib, prefix, panel, size, recombrate=1.26, effective_N=
     if st != 0:
         raise RuntimeError(getattr(lib, prefix + "last_error")().decode())
     return paths, scores, p2a, nk, counts[:int(nk.sum())]
+
+
+def oracle_unique_kmers(lib, graph_counter: "OracleCounter", flat: dict):
+    """pgo_unique_kmers_compute over the flat arrays of tests/refgraph.flatten -> Panel (index stage)."""
+    from pangenie_b200.model import panel_from_struct, variants_struct
+    vs, _keep = variants_struct(flat)
+    h = lib.pgo_unique_kmers_compute(graph_counter.h, C.byref(vs))
+    if not h:
+        raise RuntimeError("pgo_unique_kmers_compute failed (an undefined allele that no path carries?)")
+    try:
+        ps = PgPanel()
+        assert lib.pgo_unique_kmers_panel(h, C.byref(ps)) == 0
+        return panel_from_struct(ps)
+    finally:
+        lib.pgo_unique_kmers_free(h)
