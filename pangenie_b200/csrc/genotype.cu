@@ -540,7 +540,7 @@ static bool try_cluster_skeleton(const ChainParams& p, uint32_t n_chrom, int cfg
 // shared-memory reads one SM spends per column, and both fall with the number of warps a chain is spread over (every lane
 // reads the row sum of each of its columns once per column: lanes that own whole rows share those reads as broadcasts).
 // The dense checkpoints are independent of the tile configuration, so the block kernel keeps its own.
-// PG_SKELETON_TILE = 0 (the block kernel's configuration), 1 (one lane per row) or 2 (two lanes per row).
+// PG_SKELETON_TILE = 0 (the block kernel's configuration), 1 (one lane per row), 2 (two lanes per row) or 3 (lean walk).
 template <int L, int CPL, int NT>
 static cudaError_t launch_rowlane(const ChainParams& p, uint32_t n_chrom, cudaStream_t s) {
   skeleton_kernel<L, CPL, 1, NT><<<dim3(n_chrom, 2), NT, sizeof(ChainSmem), s>>>(p);
@@ -557,6 +557,21 @@ static bool try_rowlane_skeleton(const ChainParams& p, uint32_t n_chrom, cudaStr
     if (P > 16 && P <= 33) err = launch_rowlane<1, 33, 64>(p, n_chrom, s);
     else if (P > 33 && P <= 65) err = launch_rowlane<1, 65, 96>(p, n_chrom, s);
     else return false;
+    return true;
+  }
+  if (mode == 3) {  // lean walk (hmm_kernels.cuh skeleton_lean_kernel): TMA descriptor ring, one row per thread
+    const size_t smem = ((sizeof(ChainSmem) + 15) & ~size_t(15)) + HMM_NSLOT * 8;
+    const dim3 grid(n_chrom, 2);
+    if (P > 16 && P <= 34) {
+      if (34 - P <= 4) skeleton_lean_kernel<2, 17, 96, 4><<<grid, 96, smem, s>>>(p);
+      else skeleton_lean_kernel<2, 17, 96, 17><<<grid, 96, smem, s>>>(p);
+    } else if (P > 34 && P <= 68) {
+      if (68 - P <= 4) skeleton_lean_kernel<4, 17, 288, 4><<<grid, 288, smem, s>>>(p);
+      else skeleton_lean_kernel<4, 17, 288, 17><<<grid, 288, smem, s>>>(p);
+    } else {
+      return false;
+    }
+    err = cudaGetLastError();
     return true;
   }
   if (mode == 2) {

@@ -539,6 +539,267 @@ __global__ void __launch_bounds__(NT) skeleton_kernel(const ChainParams p) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// phase 1, LEAN walk (one row per thread, L = 2 or 4 lanes per row, CPL = 17 columns per lane: P <= 34 / P <= 68).
+//
+// What bounds the walk (profiles/r2_skeleton.md): one chain = one CTA = one or two warps per scheduler, so the schedulers
+// have nothing to switch to and every dependent instruction costs its full latency - measured on B200
+// (scripts/microbench/latency.cu): fp64 op 8 cycles, one shuffle level of a double 35, shared store -> barrier -> load
+// 50-60.  The generic walk above spends ~1450 cycles per column at P = 33 WHATEVER its tile shape; its source-level profile
+// shows where: ~400 instructions per warp and column around 4 fp64 operations per cell (selects, address arithmetic,
+// re-materialised shared-window bases), the descriptor prefetch (address arithmetic + cp.async + wait_group in warp 0 while
+// the other warps sit at the barrier) and the loads of the next record.  This kernel removes those:
+//   * descriptor records arrive by TMA: ONE elected thread issues `cp.async.bulk` (global -> shared, 336 B at P = 33) per
+//     column, 6 columns ahead, completion through one mbarrier per ring slot (complete_tx); consumers `try_wait` on the slot's
+//     phase - no per-lane address arithmetic, no wait_group, and completion makes the record visible without a CTA barrier;
+//   * the record of column t+1 is read at the TOP of column t (software pipelining): its shared-memory latency overlaps the
+//     row-sum loads of column t;
+//   * the 17 row sums of the thread's columns are loaded once; their sum, completed by log2(L) shuffle levels, IS the total
+//     (every lane group adds the same numbers in the same order: bitwise the same T, hence the same power-of-two scale, in
+//     every thread);
+//   * 4 fp64 operations + one select per cell; only the trailing NMASK cells carry the "column < P" select;
+//   * shared memory is addressed through a 32-bit base taken once (no S2R / LEA re-materialisation in the loop);
+//   * the dead-column case (total == 0 -> uniform) is branch-free.
+// Columns with more than two alleles take the generic step (same registers, same shared-memory row sums).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  unsigned long long a;
+  asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
+  return (uint32_t)a;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds_v2f64(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds_v2u64(uint32_t a, unsigned long long& x, unsigned long long& y) {
+  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// one descriptor record, global -> shared, by the TMA engine; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void tma_load_record(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct LeanCol {  // chain-independent inputs of one column
+  double da, db, dc, dk, er0, er1;
+  uint32_t jb, A;
+};
+
+template <int L, int CPL, int NT>
+struct LeanCtx {
+  uint32_t rs_base;    // shared address of sm->rs[0][0]
+  uint32_t desc_base;  // shared address of sm->desc[0]
+  uint32_t bar_base;   // shared address of the 8 slot mbarriers
+  uint32_t phase;      // bit s: parity to wait for on slot s
+  int col0, row, lc;
+  bool rok;
+  double invS;
+};
+
+template <bool BACKWARD, int L, int CPL, int NT>
+__device__ __forceinline__ void lean_load(LeanCtx<L, CPL, NT>& cx, int slot, LeanCol& c) {
+  mbar_wait(cx.bar_base + 8u * (uint32_t)slot, (cx.phase >> slot) & 1u);
+  cx.phase ^= 1u << slot;
+  const uint32_t d = cx.desc_base + (uint32_t)slot * (uint32_t)(DESC_SLOT_WORDS * 8);
+  const uint32_t o = BACKWARD ? 32u : 0u;
+  lds_v2f64(d + o, c.da, c.db);
+  lds_v2f64(d + o + 16u, c.dc, c.dk);
+  c.A = lds_u32(d + 64u);
+  double e00, e01, e10, e11;
+  lds_v2f64(d + 80u, e00, e01);
+  lds_v2f64(d + 112u, e10, e11);
+  unsigned long long w0, w1;
+  lds_v2u64(d + (uint32_t)(DESC_BITS_AT * 8), w0, w1);  // allele bits of paths 0..127 (P <= 68 here)
+  const int c0 = cx.col0;
+  unsigned long long lo = c0 < 64 ? (w0 >> c0) : (w1 >> (c0 - 64));
+  if (c0 > 0 && c0 < 64) lo |= w1 << (64 - c0);
+  c.jb = (uint32_t)lo;
+  const uint32_t ib = (uint32_t)(((cx.row < 64 ? w0 : w1) >> (cx.row & 63)) & 1ull);
+  c.er0 = cx.rok ? (ib ? e10 : e00) : 0.0;
+  c.er1 = cx.rok ? (ib ? e11 : e01) : 0.0;
+}
+
+template <bool BACKWARD, int NMASK, int L, int CPL, int NT>
+__device__ __forceinline__ void lean_step(Chain<L, CPL, 1, NT>& ch, const LeanCtx<L, CPL, NT>& cx, const LeanCol& c, int cbuf, int nbuf) {
+  const uint32_t ra = cx.rs_base + (uint32_t)(cbuf * HMM_RS_PAD + cx.col0) * 8u;
+  double rj[CPL];
+#pragma unroll
+  for (int s = 0; s < CPL; ++s) rj[s] = lds_f64(ra + 8u * s);  // zero beyond P
+  double t0 = rj[0], t1 = rj[1], t2 = rj[2], t3 = rj[3];
+#pragma unroll
+  for (int s = 4; s < CPL; ++s) {
+    if ((s & 3) == 0) t0 += rj[s];
+    else if ((s & 3) == 1) t1 += rj[s];
+    else if ((s & 3) == 2) t2 += rj[s];
+    else t3 += rj[s];
+  }
+  double T = (t0 + t1) + (t2 + t3);
+#pragma unroll
+  for (int o = 1; o < L; o <<= 1) T += __shfl_xor_sync(0xffffffffu, T, o);
+  // previous column underflowed (T == 0) -> uniform replacement (hmm.cpp:258-260 / :377-379), without a branch
+  const bool live = T > 0.0;
+  const double sc = pow2_scale_of(live ? T : 1.0);
+  const double ca = live ? c.da * sc : 0.0;
+  const double cb = live ? c.db * sc : 0.0;
+  const double cc = live ? c.dc * T * sc : (BACKWARD ? cx.invS : c.dk * cx.invS);
+  const double rho = fma(cb, ch.rrow[0], cc);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int s = 0; s < CPL; ++s) {
+    const double pre = fma(ca, ch.x[0][s], fma(cb, rj[s], rho));
+    double v = pre * (((c.jb >> s) & 1u) ? c.er1 : c.er0);
+    if (s >= CPL - NMASK) v = ((ch.vmask >> s) & 1u) ? v : 0.0;  // columns beyond P: trailing cells of the last lane group
+    ch.x[0][s] = v;
+    if ((s & 3) == 0) a0 += v;
+    else if ((s & 3) == 1) a1 += v;
+    else if ((s & 3) == 2) a2 += v;
+    else a3 += v;
+  }
+  double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  ch.rrow[0] = acc;
+  if (cx.lc == 0 && cx.rok) sts_f64(cx.rs_base + (uint32_t)(nbuf * HMM_RS_PAD + cx.row) * 8u, acc);
+}
+
+constexpr int LEAN_AHEAD = 6;  // records in flight ahead of the column being computed (ring of HMM_NSLOT = 8)
+
+template <int L, int CPL, int NT, int NMASK>
+__global__ void __launch_bounds__(NT) skeleton_lean_kernel(const ChainParams p) {
+  static_assert(CPL <= 32 && L * CPL <= 128, "allele bits of a lane's columns must fit one word; paths must fit two mask words");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChainSmem* sm = reinterpret_cast<ChainSmem*>(smem_raw);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(ChainSmem) + 15) & ~size_t(15)));
+  Chain<L, CPL, 1, NT> ch;
+  ch.init(sm, &p);
+  const ChromCols cc = p.chroms[blockIdx.x];
+  if (cc.n_blocks <= 1) return;
+  if (p.seq_flags && !p.seq_flags[blockIdx.x]) return;
+  LeanCtx<L, CPL, NT> cx;
+  cx.rs_base = smem_addr(&sm->rs[0][0]);
+  cx.desc_base = smem_addr(&sm->desc[0][0]);
+  cx.bar_base = smem_addr(bars);
+  cx.phase = 0;
+  cx.col0 = ch.col0;
+  cx.row = ch.row(0);
+  cx.lc = ch.lc;
+  cx.rok = cx.row < ch.row_lim;
+  cx.invS = 1.0 / ((double)ch.P * (double)ch.P);
+  for (int i = threadIdx.x; i < 2 * HMM_RS_PAD; i += NT) (&sm->rs[0][0])[i] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HMM_NSLOT; ++i) mbar_init(cx.bar_base + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int c0 = (int)cc.col_begin, c1 = (int)cc.col_end, B = (int)p.B;
+  const size_t CS = p.ckpt_stride;
+  const uint32_t rec = p.desc_stride;
+  double nou[1][CPL];
+  LeanCol col;
+  int cur = 0;
+  auto issue = [&](int t) {  // elected thread: record of column t -> ring slot t & 7
+    const uint32_t sl = (uint32_t)(t & (HMM_NSLOT - 1));
+    tma_load_record(cx.desc_base + sl * (uint32_t)(DESC_SLOT_WORDS * 8), p.desc + (size_t)(uint32_t)t * rec, rec, cx.bar_base + 8u * sl);
+  };
+  if (blockIdx.y == 0) {
+    const int last = c0 + (int)(cc.n_blocks - 1) * B - 1;   // columns c0 .. last are walked
+    if (threadIdx.x == 0)
+      for (int t = c0; t <= last && t <= c0 + LEAN_AHEAD; ++t) issue(t);
+    int slot = ch.slot_of(c0);
+    mbar_wait(cx.bar_base + 8u * (uint32_t)slot, 0);
+    cx.phase ^= 1u << slot;
+    ch.template step<false, true, false>(slot, 0, 0, 0.0, nou, 0);
+    slot = ch.slot_next(slot);
+    if (c0 + 1 <= last) lean_load<false>(cx, slot, col);
+    __syncthreads();
+    int until_ckpt = B - 1;
+    uint32_t blk = cc.blk_begin + 1;
+    for (int t = c0 + 1; t <= last; ++t) {
+      // the slot of record t-2 is free (its last reader passed the barrier of column t-1): refill it with record t+6
+      if (threadIdx.x == 0 && t + LEAN_AHEAD <= last) issue(t + LEAN_AHEAD);
+      const LeanCol cur_col = col;
+      const int nslot = ch.slot_next(slot);
+      if (t < last) lean_load<false>(cx, nslot, col);  // record of column t+1, overlapped with the step below
+      if (until_ckpt == 0) {
+        ch.store_dense(p.ckpt_fwd + (size_t)blk * CS);
+        ++blk;
+        until_ckpt = B;
+      }
+      --until_ckpt;
+      if (cur_col.A <= 2) {
+        lean_step<false, NMASK>(ch, cx, cur_col, cur, cur ^ 1);
+      } else {
+        const double T = ch.total(cur);
+        ch.template step<false, false, false>(slot, cur, cur ^ 1, T, nou, 0);
+      }
+      slot = nslot;
+      __syncthreads();
+      cur ^= 1;
+    }
+    ch.store_dense(p.ckpt_fwd + (size_t)(cc.blk_begin + cc.n_blocks - 1) * CS);
+  } else {
+    const int first = c0 + B;                               // columns c1-1 .. first are walked
+    if (threadIdx.x == 0)
+      for (int t = c1 - 1; t >= first && t >= c1 - 1 - LEAN_AHEAD; --t) issue(t);
+    int slot = ch.slot_of(c1 - 1);
+    mbar_wait(cx.bar_base + 8u * (uint32_t)slot, 0);
+    cx.phase ^= 1u << slot;
+    ch.template step<true, true, false>(slot, 0, 0, 0.0, nou, 0);
+    int rel = (c1 - 1 - c0) % B;
+    uint32_t blk = cc.blk_begin + (uint32_t)((c1 - 1 - c0) / B);
+    if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
+    slot = ch.slot_prev(slot);
+    if (c1 - 2 >= first) lean_load<true>(cx, slot, col);
+    __syncthreads();
+    for (int t = c1 - 2; t >= first; --t) {
+      if (threadIdx.x == 0 && t - LEAN_AHEAD >= first) issue(t - LEAN_AHEAD);
+      const LeanCol cur_col = col;
+      const int nslot = ch.slot_prev(slot);
+      if (t > first) lean_load<true>(cx, nslot, col);
+      if (rel == 0) {
+        rel = B;
+        --blk;
+      }
+      --rel;
+      if (cur_col.A <= 2) {
+        lean_step<true, NMASK>(ch, cx, cur_col, cur, cur ^ 1);
+      } else {
+        const double T = ch.total(cur);
+        ch.template step<true, false, false>(slot, cur, cur ^ 1, T, nou, 0);
+      }
+      if (rel == 0) ch.store_dense(p.ckpt_bwd + (size_t)(blk - 1) * CS);
+      slot = nslot;
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // phase 1 over a thread-block CLUSTER.  The walk above is bound by what one SM can issue and move per column (ncu at
 // P = 65: 2300 cycles per column with 9 warps, issue + shared-memory pipes; shortening or re-ordering the dependent chain
 // did not move it), and the longest chromosome's walk is the critical path of the whole stage once the sample is sharded

@@ -245,7 +245,7 @@ def test_reference_catch_suite_passes_over_the_gpu_library():
     assert out.count("FAILED:") == 1
 
 
-@pytest.mark.parametrize("n_paths", [1, 2, 3, 8, 9, 10, 16, 17, 20, 21, 36, 37, 40, 41, 68, 69, 72, 73, 136, 137, 256])
+@pytest.mark.parametrize("n_paths", [1, 2, 3, 8, 9, 10, 16, 17, 20, 21, 29, 30, 33, 34, 35, 36, 37, 40, 41, 63, 64, 65, 68, 69, 72, 73, 136, 137, 256])
 def test_path_counts_at_kernel_configuration_boundaries(engine, oracle, n_paths):
     """Every tile configuration of the chain kernels at its smallest and largest path count (csrc/genotype.cu pick_cfg),
     several checkpoint blocks each, multi-allelic and undefined alleles included."""
