@@ -536,51 +536,33 @@ static bool try_cluster_skeleton(const ChainParams& p, uint32_t n_chrom, int cfg
   return false;
 }
 
-// Checkpoint walk with FEW lanes per row (hmm_kernels.cuh, "row-per-lane"): the walk is bound by the instructions and
-// shared-memory reads one SM spends per column, and both fall with the number of warps a chain is spread over (every lane
-// reads the row sum of each of its columns once per column: lanes that own whole rows share those reads as broadcasts).
-// The dense checkpoints are independent of the tile configuration, so the block kernel keeps its own.
-// PG_SKELETON_TILE = 0 (the block kernel's configuration), 1 (one lane per row), 2 (two lanes per row) or 3 (lean walk).
-template <int L, int CPL, int NT>
-static cudaError_t launch_rowlane(const ChainParams& p, uint32_t n_chrom, cudaStream_t s) {
-  skeleton_kernel<L, CPL, 1, NT><<<dim3(n_chrom, 2), NT, sizeof(ChainSmem), s>>>(p);
-  return cudaGetLastError();
-}
+// Checkpoint walk of 16 < P <= 68 paths: the LEAN walk of hmm_kernels.cuh (TMA descriptor ring, one row per thread, 17 columns
+// per lane).  PG_SKELETON_TILE = 0 selects the generic walk (the block kernel's tile configuration) instead.
+// Measured per 400 k columns (scripts/bench_hmm.py, profiles/r2_skeleton.md): H = 32 24.0 -> 15.0 ms, H = 64 37.6 -> 28.8 ms.
+// Not kept (measured, no gain): the generic walk instantiated with one / two lanes per row (23.3 / 27.2 ms at H = 32, and the
+// different summation order of whole rows in one thread cost 7e-6 relative on one oracle case), 9 columns per lane for the
+// lean walk (16.9 / 37.0 ms), the walk split over a thread-block cluster (38 / 42-47 ms; kept as PG_SKELETON_CLUSTER).
 #ifndef PG_SKELETON_TILE_DEFAULT
-#define PG_SKELETON_TILE_DEFAULT 0
+#define PG_SKELETON_TILE_DEFAULT 3
 #endif
-static bool try_rowlane_skeleton(const ChainParams& p, uint32_t n_chrom, cudaStream_t s, cudaError_t& err) {
+static bool try_lean_skeleton(const ChainParams& p, uint32_t n_chrom, cudaStream_t s, cudaError_t& err) {
   const char* e = getenv("PG_SKELETON_TILE");
   const int mode = e ? atoi(e) : PG_SKELETON_TILE_DEFAULT;
   const int P = (int)p.P;
-  if (mode == 1) {
-    if (P > 16 && P <= 33) err = launch_rowlane<1, 33, 64>(p, n_chrom, s);
-    else if (P > 33 && P <= 65) err = launch_rowlane<1, 65, 96>(p, n_chrom, s);
-    else return false;
-    return true;
+  if (mode != 3) return false;
+  const size_t smem = ((sizeof(ChainSmem) + 15) & ~size_t(15)) + HMM_NSLOT * 8;
+  const dim3 grid(n_chrom, 2);
+  if (P > 16 && P <= 34) {
+    if (34 - P <= 4) skeleton_lean_kernel<2, 17, 96, 4><<<grid, 96, smem, s>>>(p);
+    else skeleton_lean_kernel<2, 17, 96, 17><<<grid, 96, smem, s>>>(p);
+  } else if (P > 34 && P <= 68) {
+    if (68 - P <= 4) skeleton_lean_kernel<4, 17, 288, 4><<<grid, 288, smem, s>>>(p);
+    else skeleton_lean_kernel<4, 17, 288, 17><<<grid, 288, smem, s>>>(p);
+  } else {
+    return false;
   }
-  if (mode == 3) {  // lean walk (hmm_kernels.cuh skeleton_lean_kernel): TMA descriptor ring, one row per thread
-    const size_t smem = ((sizeof(ChainSmem) + 15) & ~size_t(15)) + HMM_NSLOT * 8;
-    const dim3 grid(n_chrom, 2);
-    if (P > 16 && P <= 34) {
-      if (34 - P <= 4) skeleton_lean_kernel<2, 17, 96, 4><<<grid, 96, smem, s>>>(p);
-      else skeleton_lean_kernel<2, 17, 96, 17><<<grid, 96, smem, s>>>(p);
-    } else if (P > 34 && P <= 68) {
-      if (68 - P <= 4) skeleton_lean_kernel<4, 17, 288, 4><<<grid, 288, smem, s>>>(p);
-      else skeleton_lean_kernel<4, 17, 288, 17><<<grid, 288, smem, s>>>(p);
-    } else {
-      return false;
-    }
-    err = cudaGetLastError();
-    return true;
-  }
-  if (mode == 2) {
-    if (P > 16 && P <= 34) err = launch_rowlane<2, 17, 96>(p, n_chrom, s);
-    else if (P > 34 && P <= 66) err = launch_rowlane<2, 33, 160>(p, n_chrom, s);
-    else return false;
-    return true;
-  }
-  return false;
+  err = cudaGetLastError();
+  return true;
 }
 
 template <int L, int CPL, int RPW, int NT>
@@ -1131,7 +1113,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     }
     if (need_skel) {
       le = cudaSuccess;
-      if (!try_rowlane_skeleton(cp, e->n_chrom, s, le) && !try_cluster_skeleton(cp, e->n_chrom, cfg.id, s, le)) { PG_DISPATCH(true, false) }
+      if (!try_cluster_skeleton(cp, e->n_chrom, cfg.id, s, le) && !try_lean_skeleton(cp, e->n_chrom, s, le)) { PG_DISPATCH(true, false) }
       if (le != cudaSuccess) return fail(PG_ERR_CUDA, std::string("skeleton_kernel launch: ") + cudaGetErrorString(le));
       count_launch();
     }

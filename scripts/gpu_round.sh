@@ -80,10 +80,12 @@ ncu_hmm)
   PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"skeleton_kernel|block_kernel" -s 1 -c 2 -o $out/prof_hmm_$tag \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3s} > $out/ncu_hmm_$tag.out 2>&1; tail -3 $out/ncu_hmm_$tag.out;;
 sanitizer)
-  timeout 1200 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_hmm.py tests/test_gpu_counting.py tests/test_gpu_at_size.py -m gpu -q -p no:cacheprovider \
-     -k "reference_vector or edge_cases or options or kmercounter_vectors or scan_and_sequential or partitioned or canonical or long_headers or subsets" 2>&1 | tail -60 > $out/sanitizer_$tag.log; tail -8 $out/sanitizer_$tag.log;;
+  timeout 1200 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_hmm.py tests/test_gpu_counting.py tests/test_gpu_at_size.py tests/test_index_build.py tests/test_demo_config0.py -m gpu -q -p no:cacheprovider \
+     -k "reference_vector or edge_cases or options or kmercounter_vectors or scan_and_sequential or partitioned or canonical or long_headers or subsets or lean or device_selection or demo" 2>&1 | tail -60 > $out/sanitizer_$tag.log; tail -8 $out/sanitizer_$tag.log;;
 racecheck)
-  timeout 1200 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_hmm.py tests/test_gpu_counting.py -m gpu -q -p no:cacheprovider \
-     -k "reference_vector or kmercounter_vectors or scan_and_sequential or partitioned" 2>&1 | tail -60 > $out/racecheck_$tag.log; tail -8 $out/racecheck_$tag.log;;
+  timeout 1200 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_hmm.py tests/test_gpu_counting.py tests/test_index_build.py -m gpu -q -p no:cacheprovider \
+     -k "reference_vector or kmercounter_vectors or scan_and_sequential or partitioned or lean or reference_index_fixture" 2>&1 | tail -60 > $out/racecheck_$tag.log; tail -8 $out/racecheck_$tag.log;;
+bench_index)
+  timeout 900 python scripts/bench_index.py --variants ${IDXV:-1000000} > $out/bench_index_$tag.json 2> $out/bench_index_$tag.err; cat $out/bench_index_$tag.json; tail -3 $out/bench_index_$tag.err;;
 esac
 done

@@ -281,6 +281,7 @@ def test_cluster_checkpoint_walk_is_bitwise_identical(engine, oracle, monkeypatc
         c = [(10, 10), (20, 0), (0, 20), (10, 0)][int(rng.integers(0, 4))]
         b.insert_kmer(v, c[0], [0]); b.insert_kmer(v, c[1], [1])
     dead = b.build()
+    monkeypatch.setenv("PG_SKELETON_TILE", "0")   # the cluster walk shares its step with the generic walk, not with the lean one
     for p, t, kw in ((panel, _table(), dict(recombrate=1.26, effective_N=1e-5)), (dead, probs, dict(recombrate=1.26, effective_N=25000.0))):
         monkeypatch.setenv("PG_SKELETON_CLUSTER", "0")
         one = engine.hmm_run([p, p], t, **kw)
@@ -291,3 +292,45 @@ def test_cluster_checkpoint_walk_is_bitwise_identical(engine, oracle, monkeypatc
             got = engine.hmm_run([p, p], t, **kw)
             for g, o in zip(got, one):
                 assert np.array_equal(g.likelihoods, o.likelihoods) and np.array_equal(g.genotype, o.genotype), (n_paths, C)
+
+
+@pytest.mark.parametrize("n_paths", [17, 25, 33, 34, 35, 50, 65, 68])
+def test_lean_checkpoint_walk_matches_generic_walk_and_oracle(engine, oracle, monkeypatch, n_paths):
+    """The lean checkpoint walk (TMA descriptor ring + mbarriers, csrc/hmm_kernels.cuh skeleton_lean_kernel; the default for
+    16 < P <= 68) against the generic walk (PG_SKELETON_TILE=0) and the oracle: multi-allelic columns (generic step inside the lean
+    kernel), undefined alleles, columns whose total is exactly zero (uniform replacement, branch-free in the lean step),
+    several chromosomes of different lengths in one call (chains shorter than the descriptor ring included)."""
+    rng = np.random.default_rng(900 + n_paths)
+    panels = [random_panel(rng, n, n_paths, max_alleles=3, undefined_frac=0.05, ref_only_frac=0.02, kmers_per_allele=(0, 8))
+              for n in (700, 150, 9, 3)]
+    probs = pg.ProbabilityTable(0, 1, 21, 0.0)   # exact zeros: some column totals are exactly zero
+    probs.modify_probability(0, 10, 0.0, 1.0, 0.0)
+    probs.modify_probability(0, 20, 0.0, 0.0, 1.0)
+    probs.modify_probability(0, 0, 1.0, 0.0, 0.0)
+    b = pg.PanelBuilder()
+    pos = 1000
+    for i in range(400):
+        pos += int(rng.integers(100, 2000))
+        al = rng.integers(0, 2, size=n_paths)
+        al[0], al[1] = 0, 1
+        v = b.add_variant(pos, al)
+        c = [(10, 10), (20, 0), (0, 20), (10, 0)][int(rng.integers(0, 4))]
+        b.insert_kmer(v, c[0], [0]); b.insert_kmer(v, c[1], [1])
+    dead = [b.build()]
+    for ps, t, kw, blk in ((panels, _table(), dict(recombrate=1.26, effective_N=1e-5), None),
+                           (panels, _table(), dict(recombrate=1.26, effective_N=1e-5), "3"),     # many checkpoints, chains of 1-3 blocks
+                           (dead, probs, dict(recombrate=1.26, effective_N=25000.0), "7")):
+        if blk is None:
+            monkeypatch.delenv("PG_HMM_B", raising=False)
+        else:
+            monkeypatch.setenv("PG_HMM_B", blk)
+        want = oracles.cpu_hmm_run(oracle, "pgo_", ps, t, **kw)
+        monkeypatch.setenv("PG_SKELETON_TILE", "0")
+        generic = engine.hmm_run(ps, t, **kw)
+        monkeypatch.setenv("PG_SKELETON_TILE", "3")
+        lean = engine.hmm_run(ps, t, **kw)
+        for g, l, w in zip(generic, lean, want):
+            assert_results_close(l, w, atol=1e-300, label=f"lean P={n_paths}")
+            assert_results_close(g, w, atol=1e-300, label=f"generic P={n_paths}")
+            assert np.array_equal(g.genotype, l.genotype)
+            np.testing.assert_allclose(l.likelihoods, g.likelihoods, rtol=1e-9, atol=1e-300)
