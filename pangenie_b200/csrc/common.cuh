@@ -1,6 +1,7 @@
 // Shared host/device helpers of libpangenie_b200 (sm_100a only; no CPU fallback anywhere).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <functional>
@@ -28,6 +29,15 @@ int last_code();  // status code of the last fail() on this thread
     int st_ = (call);             \
     if (st_ != PG_OK) return st_; \
   } while (0)
+
+/** NVTX range around a host-side stage of the path (header-only NVTX 3: a no-op unless a profiler is attached), so that
+ *  nsys / ncu timelines show count / histogram / fill / emission+HMM / fetch of every call. */
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DeviceGuard {
   int prev = -1;

@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) desc_build_kernel(PanelDev pd, const uint
                                                           const uint32_t* __restrict__ col_variant, const uint32_t* __restrict__ col_chrom_end,
                                                           const uint32_t* __restrict__ col_chrom_begin, uint32_t n_cols,
                                                           const uint64_t* __restrict__ em_off, const double* __restrict__ em,
-                                                          TransParams tp, uint8_t* __restrict__ desc, uint32_t stride) {
+                                                          TransParams tp, const uint64_t* __restrict__ gl_off, uint8_t* __restrict__ desc,
+                                                          uint32_t stride) {
   const int lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_cols; t += warps) {
@@ -224,7 +225,16 @@ __global__ void __launch_bounds__(256) desc_build_kernel(PanelDev pd, const uint
       uint32_t* h = reinterpret_cast<uint32_t*>(d + 8);
       h[0] = A;
       h[1] = v;
-      *reinterpret_cast<unsigned long long*>(d + 9) = (unsigned long long)(em + em_off[v]);
+      // [9]: columns with more than HMM_FAST_A alleles: pointer to the emission table; others: the allele ids of the (up to
+      // four) allele indices, 16 bits each.  [31]: offset of the variant's posterior row.  With both in the record the posterior
+      // writer of the block kernel needs no dependent global loads (allele_off -> allele_ids, gl_off) on its column's path.
+      unsigned long long w9 = (unsigned long long)(em + em_off[v]);
+      if (A <= HMM_FAST_A) {
+        w9 = 0;
+        for (uint32_t i = 0; i < A; ++i) w9 |= (unsigned long long)pd.allele_ids[ab + i] << (16 * i);
+      }
+      *reinterpret_cast<unsigned long long*>(d + 9) = w9;
+      *reinterpret_cast<unsigned long long*>(d + 31) = gl_off[v];
     }
     if (lane < 16) {
       const uint32_t i1 = lane >> 2, i2 = lane & 3;
@@ -245,7 +255,6 @@ __global__ void __launch_bounds__(256) desc_build_kernel(PanelDev pd, const uint
       const unsigned b = __ballot_sync(0xffffffffu, (idx & 1u) != 0);
       if (lane == 0) reinterpret_cast<unsigned*>(bits)[q0 >> 5] = b;
     }
-    if (lane == 0) d[31] = 0.0;
   }
 }
 
@@ -741,6 +750,7 @@ static int upload_offsets(DevBuf<uint32_t>& dst, uint32_t n_chrom, const pg_pane
 
 static int engine_load_panels(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, const pg_hmm_result* layouts,
                               bool need_counts, bool need_codes) {
+  pg::NvtxRange nvtx_("pg: load panels");
   if (!e || !panels || n_chrom == 0) return fail(PG_ERR_ARG, "invalid panel arguments");
   DeviceGuard g(e->device);
   const uint32_t P = panels[0].n_paths;
@@ -873,6 +883,7 @@ static int run_emission(pg_engine* e, const TableDev& td) {
 
 // ---- forward-backward over the loaded panel (counts + coverage resident) -------------------------------
 static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_params* prm, int fin_mode = 0) {
+  pg::NvtxRange nvtx_("pg: emission + forward-backward");
   DeviceGuard g(e->device);
   cudaStream_t s = e->stream;
   const uint32_t V = e->V, Pfull = e->P;
@@ -997,7 +1008,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
     TransParams tp{prm->recombrate, prm->effective_N, prm->uniform};
     const int grid = (int)std::min<uint64_t>(((uint64_t)C * 32 + 255) / 256, (uint64_t)e->sm_count * 16);
     desc_build_kernel<<<grid, 256, 0, s>>>(panel_view(e), e->sel.p, P, e->col_variant.p, e->col_cend.p, e->col_cbeg.p, C,
-                                            e->em_off.p, e->em.p, tp, e->desc.p, stride);
+                                            e->em_off.p, e->em.p, tp, e->gl_off.p, e->desc.p, stride);
     count_launch();
     PG_CUDA(cudaGetLastError());
     cudaEventRecord(e->ev[3], s);
@@ -1164,6 +1175,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
 }
 
 static int engine_fetch_results(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, pg_hmm_result* results) {
+  pg::NvtxRange nvtx_("pg: fetch results");
   DeviceGuard g(e->device);
   cudaStream_t s = e->stream;
   for (uint32_t c = 0; c < n_chrom; ++c) {
@@ -1183,6 +1195,7 @@ static int engine_fetch_results(pg_engine* e, uint32_t n_chrom, const pg_panel* 
 }
 
 static int engine_fill(pg_engine* e, const pg_counter* c, uint64_t peak) {
+  pg::NvtxRange nvtx_("pg: fill counts");
   if (!e->has_codes) return fail(PG_ERR_ARG, "panel was loaded without k-mer codes");
   if (c->device != e->device) return fail(PG_ERR_ARG, "counter and engine live on different devices");
   DeviceGuard g(e->device);
@@ -1360,6 +1373,7 @@ extern "C" int pg_fill_counts(pg_engine* e, const pg_counter* c, uint64_t kmer_a
 
 extern "C" int pg_genotype_run(pg_engine* e, const pg_genotype_input* in, uint32_t n_chrom, pg_panel* panels,
                                const pg_hmm_params* params, pg_hmm_result* results, uint64_t* kmer_abundance_peak) {
+  pg::NvtxRange nvtx_("pg_genotype_run");
   clear_error();
   if (!e || !in || !panels || !params || !results) return fail(PG_ERR_ARG, "null argument");
   const uint64_t l0 = g_launches;
@@ -1456,6 +1470,7 @@ extern "C" int pg_engine_load(pg_engine* e, uint32_t n_chrom, const pg_panel* pa
 extern "C" int pg_engine_run_resident(pg_engine* e, const char* d_reads, uint64_t reads_len, const char* d_segments,
                                       uint64_t segments_len, uint32_t k, uint64_t hash_size, double regularization,
                                       const pg_hmm_params* params, uint64_t* kmer_abundance_peak) {
+  pg::NvtxRange nvtx_("pg_engine_run_resident");
   clear_error();
   if (!e || !d_reads || !params) return fail(PG_ERR_ARG, "null argument");
   if (!e->has_codes) return fail(PG_ERR_ARG, "call pg_engine_load first");

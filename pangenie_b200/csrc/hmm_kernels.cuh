@@ -40,7 +40,9 @@ constexpr int HMM_BMAX = 256;       // largest block length
 // doubles: [0..3] a,b,c,kappa of the transition (t-1 -> t); [4..7] the same for (t -> t+1);
 //          [8] header: u32 A (alleles), u32 variant index; [9] emission pointer (u64, A > HMM_FAST_A);
 //          [10..25] 4x4 emission table (row-major, allele-index space) when A <= HMM_FAST_A;
-//          [26..30] 5 x u64: bit p = allele index (0/1) of selected path p, for columns with A <= 2; [31] pad;
+//          (A <= HMM_FAST_A: [9] holds the allele ids of the allele indices instead, 16 bits each);
+//          [26..30] 5 x u64: bit p = allele index (0/1) of selected path p, for columns with A <= 2;
+//          [31] u64 offset of the variant's posterior row (gl_off[variant]);
 // then u16 aidx[P] (allele index of each selected path), padded to 16 bytes.
 constexpr int DESC_HEAD_DOUBLES = 32;
 constexpr int DESC_BITS_AT = 26;
@@ -422,10 +424,10 @@ struct Chain {
       m += __shfl_xor_sync(0xffffffffu, m, 2);
       m += __shfl_xor_sync(0xffffffffu, m, 4);
       const double mt = __shfl_sync(0xffffffffu, m, (int)(((beta << 1) | alpha) << 3));  // M[beta][alpha]
-      if (sub == 0 && alpha <= beta && beta < A) {
-        const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
-        const uint16_t* ids = prm->allele_ids + prm->allele_off[v];
-        prm->post[prm->gl_off[v] + pair_index(ids[alpha], ids[beta])] = alpha == beta ? m : m + mt;
+      if (sub == 0 && alpha <= beta && beta < A) {  // destination from the record itself: no dependent global loads
+        const unsigned long long idp = reinterpret_cast<const unsigned long long*>(d)[9];
+        const unsigned long long base = reinterpret_cast<const unsigned long long*>(d)[31];
+        prm->post[base + pair_index((uint32_t)(idp >> (16 * alpha)) & 0xffffu, (uint32_t)(idp >> (16 * beta)) & 0xffffu)] = alpha == beta ? m : m + mt;
       }
       return;
     }
@@ -436,9 +438,9 @@ struct Chain {
     m += __shfl_xor_sync(0xffffffffu, m, 16);
     const double mt = __shfl_sync(0xffffffffu, m, (int)((beta << 2) | alpha));  // M[beta][alpha]
     if (half == 0 && alpha <= beta && beta < A) {
-      const uint32_t v = reinterpret_cast<const uint32_t*>(d + 8)[1];
-      const uint16_t* ids = prm->allele_ids + prm->allele_off[v];
-      prm->post[prm->gl_off[v] + pair_index(ids[alpha], ids[beta])] = alpha == beta ? m : m + mt;
+      const unsigned long long idp = reinterpret_cast<const unsigned long long*>(d)[9];
+      const unsigned long long base = reinterpret_cast<const unsigned long long*>(d)[31];
+      prm->post[base + pair_index((uint32_t)(idp >> (16 * alpha)) & 0xffffu, (uint32_t)(idp >> (16 * beta)) & 0xffffu)] = alpha == beta ? m : m + mt;
     }
   }
 };

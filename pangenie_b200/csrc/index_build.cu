@@ -353,6 +353,7 @@ int upload(DevBuf<T>& d, const T* h, size_t n, cudaStream_t s) {
 }
 
 int compute_impl(int device, const pg_counter* gc, const pg_variants* in, pg_unique_kmers* u) {
+  NvtxRange nvtx_("pg_unique_kmers_compute");
   if (!gc || !in) return fail(PG_ERR_ARG, "null argument");
   if (in->k < 1 || in->k > 32 || in->k != gc->k) return fail(PG_ERR_ARG, "k must be in [1,32] and equal to the counter's k");
   if (in->n_paths >= 65535) return fail(PG_ERR_ARG, "number of paths exceeds 65534 (src/stepwiseuniquekmercomputer.cpp:120)");

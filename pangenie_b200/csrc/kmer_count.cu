@@ -1337,6 +1337,7 @@ static int feed_impl(pg_counter* c, const char* src, uint64_t len, int op) {
 // read chunks cross PCIe while the PRIME kernels still run.  Timings land in last_prime_ms / last_feed_ms.
 int count_prime_update(pg_counter* c, const char* segments, uint64_t segments_len, const char* reads, uint64_t reads_len,
                        const std::function<int()>* overlap) {
+  pg::NvtxRange nvtx_("pg: PRIME + UPDATE");
   if (!c) return fail(PG_ERR_ARG, "null counter");
   DeviceGuard g(c->device);
   PG_TRY(feed_enqueue(c, segments, segments_len, PG_OP_PRIME, c->ev_p0, c->ev_p1));
@@ -1440,11 +1441,13 @@ extern "C" void pg_count_destroy(pg_counter* c) {
 }
 
 extern "C" int pg_count_feed(pg_counter* c, const char* text, uint64_t len, int op) {
+  pg::NvtxRange nvtx_("pg_count_feed");
   clear_error();
   return feed_impl(c, text, len, op);
 }
 
 extern "C" int pg_count_feed_device(pg_counter* c, const char* d_text, uint64_t len, int op) {
+  pg::NvtxRange nvtx_("pg_count_feed_device");
   clear_error();
   return feed_impl(c, d_text, len, op);
 }
@@ -1636,6 +1639,7 @@ extern "C" int pg_count_kmer_coverage(const pg_counter* c, uint64_t genome_kmers
 
 extern "C" int pg_count_compute_histogram(const pg_counter* c, uint64_t max_count, int largest_peak,
                                           const char* filename, uint64_t* peak) {
+  pg::NvtxRange nvtx_("pg: histogram peak");
   clear_error();
   if (!peak) return fail(PG_ERR_ARG, "null peak");
   std::vector<uint64_t> bins(max_count + 1);

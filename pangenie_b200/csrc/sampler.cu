@@ -285,6 +285,7 @@ using namespace pg;
 extern "C" int pg_haplotype_sample(int device, const pg_panel* panel, uint32_t size, double recombrate, double effective_N,
                                    int add_reference, uint16_t allele_penalty, uint64_t* sampled_paths, uint32_t* best_scores,
                                    uint16_t* new_path_to_allele, uint32_t* new_kmer_count, uint16_t* new_counts) {
+  pg::NvtxRange nvtx_("pg_haplotype_sample");
   clear_error();
   if (!panel || !sampled_paths || !best_scores || !new_path_to_allele || !new_kmer_count || !new_counts) return fail(PG_ERR_ARG, "null argument");
   const uint32_t V = panel->n_variants, P = panel->n_paths;

@@ -1,5 +1,6 @@
 """GPU forward-backward / emission vs the CPU oracle (and the reference itself where oracle/_ref travelled).
 Bar (BASELINE.json north_star): posteriors within 1e-6 relative, identical GT calls."""
+import copy
 import os
 import subprocess
 
@@ -334,3 +335,32 @@ def test_lean_checkpoint_walk_matches_generic_walk_and_oracle(engine, oracle, mo
             assert_results_close(g, w, atol=1e-300, label=f"generic P={n_paths}")
             assert np.array_equal(g.genotype, l.genotype)
             np.testing.assert_allclose(l.likelihoods, g.likelihoods, rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("n_paths", [9, 33])
+def test_samples_batched_in_one_call_equal_separate_calls(engine, oracle, n_paths):
+    """SURVEY.md 8f row 4 (many samples on the same index, reference README.md:128): the panels of S samples go into ONE pg_hmm_run
+    call as further chromosomes - every sample's forward / backward checkpoint walks run concurrently and the block kernel pulls
+    S times the jobs.  Same structure, each sample its own counts and coverage: the batched results are bit-identical to the
+    per-sample calls, and match the oracle."""
+    rng = np.random.default_rng(4200 + n_paths)
+    base = [random_panel(rng, n, n_paths, max_alleles=3, undefined_frac=0.03, kmers_per_allele=(0, 8)) for n in (500, 260, 40)]
+    samples = []
+    for s in range(3):
+        ps = [copy.deepcopy(p) for p in base]
+        for p in ps:
+            p.kmer_counts[:] = rng.integers(0, 40, size=len(p.kmer_counts)).astype(np.uint16)
+            p.coverage[:] = rng.integers(8, 30, size=len(p.coverage)).astype(np.uint16)
+        samples.append(ps)
+    table = _table()
+    kw = dict(recombrate=1.26, effective_N=1e-5)
+    batched = engine.hmm_run([p for ps in samples for p in ps], table, **kw)
+    k = 0
+    for ps in samples:
+        alone = engine.hmm_run(ps, table, **kw)
+        want = oracles.cpu_hmm_run(oracle, "pgo_", ps, table, **kw)
+        for a, w in zip(alone, want):
+            b = batched[k]
+            k += 1
+            assert np.array_equal(a.likelihoods, b.likelihoods) and np.array_equal(a.genotype, b.genotype) and np.array_equal(a.quality, b.quality)
+            assert_results_close(b, w, atol=1e-300, label=f"batched P={n_paths}")
