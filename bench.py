@@ -280,6 +280,13 @@ def cpu_reference(spec, sample: dict, threads: int) -> dict:
         "seconds_measured": {"prime": t_prime, "update": t_update, "histogram": t_hist, "fill": t_fill, "hmm_wall": t_hmm_wall, "hmm_cpu": hmm_cpu_s},
         "seconds_whole_sample": {"prime": t_prime * fs, "update": t_update * fr, "histogram": t_hist * fs, "fill": fill_full, "hmm": hmm_full, "total": total},
         "kmer_abundance_peak": int(peak),
+        # which code each part of this baseline is: the whole-stage value mixes the reference's own emission + HMM with a
+        # PORT of the jellyfish counting path; the reference-only part is reported on its own as well
+        "parts": {"counting_fill_histogram": "port (oracle/pg_oracle.cpp: CPU restatement of the jellyfish 2.x path; libjellyfish is not in this image)",
+                  "emission_hmm": "reference (unmodified src/hmm.cpp + emission / transition / indexer classes, oracle/_ref)" if ref is not None else "port"},
+        "emission_hmm_only": {"value": V / hmm_full if hmm_full > 0 else None, "unit": "variants/s",
+                              "what": "reference emission + forward-backward alone (makespan of its one-thread-per-chromosome pool); compare with "
+                                      "variants / (emission_ms + hmm_skeleton_ms + hmm_blocks_ms + finalize_ms) of the GPU line"},
     }
 
 
