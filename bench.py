@@ -419,6 +419,17 @@ def parity_check(spec, wl, panels, peak, local):
 # ------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
+def host_mem_available():
+    """MemAvailable of /proc/meminfo in bytes (None if unreadable)."""
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
 def run_b200(args, spec, name, config, rank, world, local, W, K):
     import torch
     import pangenie_b200 as pg
@@ -505,12 +516,32 @@ def run_b200(args, spec, name, config, rank, world, local, W, K):
 
     # ---------------- e2e: pinned host buffers, copies inside the timed region ----------------
     e2e, dte = {}, None
+    # All ranks decide TOGETHER whether the host can page-lock the inputs (the ranks of a box share its memory): a rank that
+    # failed alone would leave the others in the barriers of the region, and a host driven out of memory kills the whole job.
+    need = int(reads_d.numel() + segs_d.numel()) + (2 << 30)
+    avail = host_mem_available()
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    fits = torch.tensor([1.0 if avail is None or avail / max(local_world, 1) > 1.25 * need else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
     try:
-        reads_h = torch.empty(reads_d.numel(), dtype=torch.uint8, pin_memory=True)
-        reads_h.copy_(reads_d)
-        segs_h = torch.empty(segs_d.numel(), dtype=torch.uint8, pin_memory=True)
-        segs_h.copy_(segs_d)
-        torch.cuda.synchronize()
+        if float(fits[0]) < 1.0:
+            raise RuntimeError(f"host memory: {0 if avail is None else avail / 1e9:.0f} GB available for {local_world} ranks, "
+                               f"{need / 1e9:.0f} GB of pinned buffers needed per rank")
+        alloc_err = None
+        try:
+            reads_h = torch.empty(reads_d.numel(), dtype=torch.uint8, pin_memory=True)
+            reads_h.copy_(reads_d)
+            segs_h = torch.empty(segs_d.numel(), dtype=torch.uint8, pin_memory=True)
+            segs_h.copy_(segs_d)
+            torch.cuda.synchronize()
+        except (RuntimeError, MemoryError) as ex:
+            alloc_err = ex
+        got = torch.tensor([0.0 if alloc_err is not None else 1.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(got, op=dist.ReduceOp.MIN)   # nobody enters the barriers of the region unless everybody can
+        if float(got[0]) < 1.0:
+            raise RuntimeError(f"pinned host buffers could not be allocated on some rank ({alloc_err})")
         for p in panels:  # the index arrays are uploaded every step: page-lock the large ones like the read buffers
             for nm in ("path_to_allele", "kmer_codes", "flank_codes", "positions"):
                 a = getattr(p, nm)
