@@ -1119,7 +1119,8 @@ static uint64_t part_slice_bytes() { return env_u64("PG_COUNT_PART_KB", 96u << 1
 constexpr size_t PART_CURSOR_WORDS = (size_t)MAX_PARTS * PART_REPL * CURSOR_STRIDE;   // followed by MAX_PARTS work counters
 
 // decides whether this pass is partitioned; sizes the buffers; `super` = text bytes per probe pass
-static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is_fastq, PartArgs& pa, bool& use, uint64_t& super) {
+static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, bool host_text, int is_fastq, PartArgs& pa, bool& use,
+                      uint64_t& super) {
   use = false;
   // `resident`: device text, or pinned host text behind a deep staging ring (the PCIe stream runs on while a probe pass
   // occupies the compute stream).  Text the host has to copy first arrives too slowly for partitioning to matter.
@@ -1138,6 +1139,10 @@ static int part_setup(pg_counter* c, uint64_t len, int op, bool resident, int is
     budget = std::min<uint64_t>(24ull << 30, (uint64_t)(free_b + c->part_buf_cap * 8) / 3);
   }
   uint64_t want_super = std::min<uint64_t>(len, env_u64("PG_COUNT_SUPER_MB", 1ull << 30) << 20);
+  // Text that is still crossing PCIe: the LAST probe pass runs after the last byte has arrived and overlaps with nothing, so the
+  // passes are kept short - as long as a sweep of the table is cheap next to a pass (measured on configs[2], 22 GB table: 36 /
+  // 15 / 8 / 4 passes -> end to end 803 / 818 / 816 / 857 ms, resident probe time 333 / 240 / 229 / 228 ms).
+  if (host_text && !getenv("PG_COUNT_SUPER_MB")) want_super = std::min<uint64_t>(want_super, std::max<uint64_t>(1ull << 30, table_bytes / 16));
   uint64_t kcap = (uint64_t)((double)want_super * density * slack) + n_regions * 4096;   // k-mers the buffers should hold
   if (c->part_buf_cap >= kcap) {
     kcap = c->part_buf_cap;                       // buffers of an earlier pass are large enough: keep them
@@ -1250,7 +1255,7 @@ static int feed_enqueue(pg_counter* c, const char* src, uint64_t len, int op, cu
   memset(&pa, 0, sizeof(pa));
   bool parted = false;
   uint64_t super = 0;
-  PG_TRY(part_setup(c, len, op, direct || (pinned && ring > pg_counter::NSTAGE), is_fastq, pa, parted, super));
+  PG_TRY(part_setup(c, len, op, direct || (pinned && ring > pg_counter::NSTAGE), !on_device, is_fastq, pa, parted, super));
   if (parted) step = std::min<uint64_t>(step, super);  // a chunk never exceeds what the regions are sized for
   if (parted) PG_CUDA(cudaMemsetAsync(c->d_part_cursor, 0, (size_t)pa.n_parts * PART_REPL * CURSOR_STRIDE * sizeof(uint32_t), c->stream));
   if (parted) PG_CUDA(cudaMemsetAsync(pa.work, 0, (size_t)pa.n_parts * sizeof(uint32_t), c->stream));
