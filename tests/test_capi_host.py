@@ -77,3 +77,16 @@ def test_result_layout_matches_python_model():
     ps = p.as_struct()
     assert lib.pg_result_layout(C.byref(ps), off.ctypes.data) == 0
     assert np.array_equal(off, p.result_layout())
+
+
+def test_index_selection_reports_bad_arguments_without_touching_a_device():
+    """pg_unique_kmers_compute validates its arguments before any CUDA call; errors come back as NULL +
+    pg_last_error(), like the reference's runtime_error texts."""
+    import ctypes as C
+    from pangenie_b200.capi import PgVariants
+    lib = capi.load()
+    vs = PgVariants()
+    assert not lib.pg_unique_kmers_compute(0, None, C.byref(vs))
+    assert b"null" in lib.pg_last_error()
+    assert lib.pg_unique_kmers_panel(None, None) == capi.PG_ERR_ARG
+    lib.pg_unique_kmers_free(None)   # like free(NULL)
