@@ -273,6 +273,16 @@ int pg_hmm_run_subsets(pg_engine* e, uint32_t n_chrom, const pg_panel* panels, c
                        const pg_hmm_params* params, uint32_t n_subsets, const uint32_t* subset_offsets,
                        const uint16_t* subset_paths, pg_hmm_result* results);
 
+/** Multi-sample batching (reference README.md:128, 217: one index, many samples).  `n_samples` samples that share
+ *  the panel STRUCTURE of `panels` (n_chrom chromosomes; one host copy) are genotyped by one forward-backward launch set: the
+ *  forward and backward chains of all n_samples x n_chrom (sample, chromosome) pairs walk concurrently and the block kernel pulls
+ *  the jobs of all of them.  Sample s brings kmer_counts[s*n_chrom + c] (same CSR as panels[c].kmer_counts) and
+ *  coverage[s*n_chrom + c] ([V_c]) as pg_fill_counts wrote them, and its own ProbabilityTable tables[s] (its own k-mer coverage
+ *  peak, src/commands.cpp:846).  results[s*n_chrom + c] as for pg_hmm_run.  Identical to n_samples separate pg_hmm_run calls. */
+int pg_hmm_run_samples(pg_engine* e, uint32_t n_samples, uint32_t n_chrom, const pg_panel* panels,
+                       const uint16_t* const* kmer_counts, const uint16_t* const* coverage,
+                       const pg_probtable* const* tables, const pg_hmm_params* params, pg_hmm_result* results);
+
 /** Emission tables only — `EmissionProbabilityComputer` (src/emissionprobabilitycomputer.cpp:9-34).
  *  emissions: for variant v a dense (maxA+1)x(maxA+1) row-major matrix at em_offsets[v] (maxA = largest
  *  allele id), entries for allele pairs not in the variant's allele map are 0; values are scaled by

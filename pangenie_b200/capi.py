@@ -138,7 +138,7 @@ EXPORTS = [
     "pg_engine_load", "pg_engine_run_resident", "pg_engine_fetch", "pg_engine_run_counted", "pg_hmm_run_subsets",
     "pg_index_open", "pg_index_open_archive", "pg_index_close", "pg_index_kmer_size", "pg_index_n_chromosomes",
     "pg_index_chromosome_name", "pg_index_add_reference", "pg_index_segments_path", "pg_index_panel",
-    "pg_unique_kmers_compute", "pg_unique_kmers_panel", "pg_unique_kmers_stats", "pg_unique_kmers_write_tsv", "pg_unique_kmers_free",
+    "pg_hmm_run_samples", "pg_unique_kmers_compute", "pg_unique_kmers_panel", "pg_unique_kmers_stats", "pg_unique_kmers_write_tsv", "pg_unique_kmers_free",
 ]
 
 
@@ -214,6 +214,7 @@ def bind(lib: C.CDLL, prefix: str = "pg_") -> C.CDLL:
         _sig(lib, p + "engine_destroy", None, [vp])
         _sig(lib, p + "engine_timings", i32, [vp, C.POINTER(PgTimings)])
         _sig(lib, p + "hmm_run", i32, [vp, u32, C.POINTER(PgPanel), C.POINTER(PgProbTable), C.POINTER(PgHmmParams), C.POINTER(PgHmmResult)])
+        _sig(lib, p + "hmm_run_samples", i32, [vp, u32, u32, C.POINTER(PgPanel), vp, vp, vp, C.POINTER(PgHmmParams), C.POINTER(PgHmmResult)])
         _sig(lib, p + "index_open", vp, [C.c_char_p, i32])
         _sig(lib, p + "index_open_archive", vp, [C.c_char_p])
         _sig(lib, p + "index_close", None, [vp])

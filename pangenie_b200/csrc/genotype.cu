@@ -108,10 +108,11 @@ __device__ __forceinline__ uint32_t kmer_on_allele(uint32_t k, uint32_t off, uin
 // log_scale[v] = ln max; all-zero tables report 1.0 everywhere (emissionprobabilitycomputer.cpp:24,31-34).
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) emission_kernel(PanelDev pd, TableDev T, const uint64_t* __restrict__ em_off,
-                                                        double* __restrict__ em, double* __restrict__ log_scale) {
+                                                        double* __restrict__ em, double* __restrict__ log_scale,
+                                                        uint32_t v_begin, uint32_t v_end) {
   const int lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < pd.V; v += warps) {
+  for (uint32_t v = v_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); v < v_end; v += warps) {
     const uint32_t ab = pd.allele_off[v], A = pd.allele_off[v + 1] - ab;
     const uint32_t kb = pd.kmer_off[v], K = pd.kmer_off[v + 1] - kb;
     const uint32_t cov = pd.coverage[v];
@@ -607,6 +608,9 @@ struct pg_engine {
   uint32_t n_chrom = 0, V = 0, P = 0;
   uint64_t K = 0, A = 0, F = 0;
   std::vector<uint32_t> chrom_v0;  // variant offset of each chromosome (n_chrom + 1)
+  // multi-sample batching (pg_hmm_run_samples): per-sample ProbabilityTables for the emission step of the next engine_hmm
+  const pg_probtable* const* sample_tables = nullptr;
+  uint32_t n_sample_tables = 0, chroms_per_sample = 0;
   std::vector<uint64_t> chrom_k0, chrom_gl0, chrom_f0;
   DevBuf<uint64_t> positions;
   DevBuf<uint16_t> path_to_allele, coverage, kmer_counts, allele_ids, allele_koff;
@@ -858,26 +862,53 @@ static int engine_load_panels(pg_engine* e, uint32_t n_chrom, const pg_panel* pa
   return PG_OK;
 }
 
-static int upload_table(pg_engine* e, const pg_probtable* t, TableDev& td) {
+static size_t table_entries(const pg_probtable* t) { return t->log_p ? (size_t)(t->cov_max - t->cov_min) * t->count_max * 3 : 0; }
+
+// `at`: offset (entries) inside e->log_p, which the caller has reserved
+static int upload_table(pg_engine* e, const pg_probtable* t, TableDev& td, size_t at = 0, bool reserve = true) {
   td.cov_min = t->cov_min; td.cov_max = t->cov_max; td.count_max = t->count_max; td.reg = t->regularization;
   td.log_p = nullptr;
-  const size_t n = (size_t)(t->cov_max - t->cov_min) * t->count_max * 3;
-  if (t->log_p && n) {
-    PG_TRY(e->log_p.reserve(n));
-    PG_CUDA(cudaMemcpyAsync(e->log_p.p, t->log_p, n * 8, cudaMemcpyHostToDevice, e->stream));
-    td.log_p = e->log_p.p;
+  const size_t n = table_entries(t);
+  if (n) {
+    if (reserve) PG_TRY(e->log_p.reserve(at + n));
+    PG_CUDA(cudaMemcpyAsync(e->log_p.p + at, t->log_p, n * 8, cudaMemcpyHostToDevice, e->stream));
+    td.log_p = e->log_p.p + at;
   }
   return PG_OK;
 }
 
-static int run_emission(pg_engine* e, const TableDev& td) {
+static int run_emission(pg_engine* e, const TableDev& td, uint32_t v_begin = 0, uint32_t v_end = ~0u) {
   PG_TRY(e->em.reserve(std::max<uint64_t>(e->EM, 1)));
   PG_TRY(e->log_scale.reserve(std::max<uint32_t>(e->V, 1)));
-  if (e->V == 0) return PG_OK;
-  const int grid = (int)std::min<uint64_t>(((uint64_t)e->V * 32 + 255) / 256, (uint64_t)e->sm_count * 16);
-  emission_kernel<<<grid, 256, 0, e->stream>>>(panel_view(e), td, e->em_off.p, e->em.p, e->log_scale.p);
+  v_end = std::min<uint32_t>(v_end, e->V);
+  if (v_begin >= v_end) return PG_OK;
+  const int grid = (int)std::min<uint64_t>(((uint64_t)(v_end - v_begin) * 32 + 255) / 256, (uint64_t)e->sm_count * 16);
+  emission_kernel<<<grid, 256, 0, e->stream>>>(panel_view(e), td, e->em_off.p, e->em.p, e->log_scale.p, v_begin, v_end);
   count_launch();
   PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
+// emission tables of the loaded panels: one ProbabilityTable for everything, or (multi-sample batching, pg_hmm_run_samples) one
+// per sample = per group of `chroms_per_table` consecutive chromosomes
+static int run_emissions(pg_engine* e, const pg_probtable* table, const pg_probtable* const* tables, uint32_t n_tables,
+                         uint32_t chroms_per_table) {
+  if (!tables) {
+    TableDev td;
+    PG_TRY(upload_table(e, table, td));
+    return run_emission(e, td);
+  }
+  size_t total = 0;
+  for (uint32_t i = 0; i < n_tables; ++i) total += table_entries(tables[i]);
+  PG_TRY(e->log_p.reserve(std::max<size_t>(total, 1)));
+  size_t at = 0;
+  for (uint32_t i = 0; i < n_tables; ++i) {
+    TableDev td;
+    PG_TRY(upload_table(e, tables[i], td, at, false));
+    at += table_entries(tables[i]);
+    const uint32_t c0 = std::min<uint32_t>(i * chroms_per_table, e->n_chrom), c1 = std::min<uint32_t>((i + 1) * chroms_per_table, e->n_chrom);
+    PG_TRY(run_emission(e, td, e->chrom_v0[c0], e->chrom_v0[c1]));
+  }
   return PG_OK;
 }
 
@@ -919,9 +950,7 @@ static int engine_hmm(pg_engine* e, const pg_probtable* table, const pg_hmm_para
   }
 
   cudaEventRecord(e->ev[0], s);
-  TableDev td;
-  PG_TRY(upload_table(e, table, td));
-  PG_TRY(run_emission(e, td));
+  PG_TRY(run_emissions(e, table, e->sample_tables, e->n_sample_tables, e->chroms_per_sample));
   cudaEventRecord(e->ev[1], s);
 
   // columns
@@ -1321,6 +1350,36 @@ extern "C" int pg_hmm_run_subsets(pg_engine* e, uint32_t n_chrom, const pg_panel
   PG_TRY(engine_load_panels(e, n_chrom, panels, results, true, false));
   PG_TRY(engine_hmm_subsets(e, table, params, n_subsets, subset_offsets, subset_paths));
   PG_TRY(engine_fetch_results(e, n_chrom, panels, results));
+  e->tm.kernel_launches = g_launches - l0;
+  return PG_OK;
+}
+
+extern "C" int pg_hmm_run_samples(pg_engine* e, uint32_t n_samples, uint32_t n_chrom, const pg_panel* panels,
+                                  const uint16_t* const* kmer_counts, const uint16_t* const* coverage,
+                                  const pg_probtable* const* tables, const pg_hmm_params* params, pg_hmm_result* results) {
+  clear_error();
+  if (!e || !panels || !kmer_counts || !coverage || !tables || !params || !results) return fail(PG_ERR_ARG, "null argument");
+  if (n_samples == 0 || n_chrom == 0) return fail(PG_ERR_ARG, "no samples or no chromosomes");
+  for (uint32_t i = 0; i < n_samples; ++i)
+    if (!tables[i]) return fail(PG_ERR_ARG, "null ProbabilityTable");
+  // S x C panel views over ONE copy of the structure on the host; every sample brings its own counts and coverages
+  std::vector<pg_panel> views((size_t)n_samples * n_chrom);
+  for (uint32_t smp = 0; smp < n_samples; ++smp)
+    for (uint32_t c = 0; c < n_chrom; ++c) {
+      const size_t i = (size_t)smp * n_chrom + c;
+      if (!kmer_counts[i] || !coverage[i]) return fail(PG_ERR_ARG, "null counts / coverage of a sample");
+      views[i] = panels[c];
+      views[i].kmer_counts = const_cast<uint16_t*>(kmer_counts[i]);
+      views[i].coverage = const_cast<uint16_t*>(coverage[i]);
+    }
+  const uint64_t l0 = g_launches;
+  memset(&e->tm, 0, sizeof(e->tm));
+  PG_TRY(engine_load_panels(e, n_samples * n_chrom, views.data(), results, true, false));
+  e->sample_tables = tables; e->n_sample_tables = n_samples; e->chroms_per_sample = n_chrom;
+  const int st = engine_hmm(e, tables[0], params);
+  e->sample_tables = nullptr; e->n_sample_tables = 0; e->chroms_per_sample = 0;
+  PG_TRY(st);
+  PG_TRY(engine_fetch_results(e, n_samples * n_chrom, views.data(), results));
   e->tm.kernel_launches = g_launches - l0;
   return PG_OK;
 }

@@ -233,6 +233,32 @@ class Engine:
         _check(self._lib, self._lib.pg_hmm_run(self._h, len(panels), pa, C.byref(table.t), C.byref(prm), ra))
         return results
 
+    def hmm_run_samples(self, panels, counts, coverages, tables, **kw):
+        """Multi-sample batching (pg_hmm_run_samples): S samples on ONE index.  `panels` = the chromosomes'
+        structure, `counts[s][c]` / `coverages[s][c]` = the filled k-mer counts / local coverages of sample s on chromosome c,
+        `tables[s]` = its ProbabilityTable.  -> results[s][c]."""
+        S, Cn = len(counts), len(panels)
+        results = [[Result(p) for p in panels] for _ in range(S)]
+        prm, _keep = hmm_params(**kw)
+        pa = self._panel_array(panels)
+        ra = (PgHmmResult * (S * Cn))()
+        kc = (C.c_void_p * (S * Cn))()
+        cv = (C.c_void_p * (S * Cn))()
+        tb = (C.POINTER(type(tables[0].t)) * S)()
+        keep = []
+        for s_ in range(S):
+            tb[s_] = C.pointer(tables[s_].t)
+            for c_ in range(Cn):
+                a = np.ascontiguousarray(counts[s_][c_], np.uint16)
+                b = np.ascontiguousarray(coverages[s_][c_], np.uint16)
+                if a.size == 0:
+                    a = np.zeros(1, np.uint16)
+                keep += [a, b]
+                kc[s_ * Cn + c_], cv[s_ * Cn + c_] = a.ctypes.data, b.ctypes.data
+                ra[s_ * Cn + c_] = results[s_][c_].as_struct()
+        _check(self._lib, self._lib.pg_hmm_run_samples(self._h, S, Cn, pa, kc, cv, tb, C.byref(prm), ra))
+        return results
+
     def hmm_run_subsets(self, panels, table: ProbabilityTable, subsets, results=None, **kw):
         """The reference's `-a` mode (src/commands.cpp:916-993): one un-normalised run per path subset, likelihoods added
         per variant (run_genotyping, :166-176), normalised at the end.  `subsets` = list of lists of path ids."""

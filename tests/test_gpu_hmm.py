@@ -364,3 +364,31 @@ def test_samples_batched_in_one_call_equal_separate_calls(engine, oracle, n_path
             k += 1
             assert np.array_equal(a.likelihoods, b.likelihoods) and np.array_equal(a.genotype, b.genotype) and np.array_equal(a.quality, b.quality)
             assert_results_close(b, w, atol=1e-300, label=f"batched P={n_paths}")
+
+
+@pytest.mark.parametrize("n_paths", [9, 33])
+def test_hmm_run_samples_shares_the_structure_and_uses_each_samples_table(engine, oracle, n_paths):
+    """pg_hmm_run_samples: one host copy of the panel structure, per sample its counts, coverages and its OWN ProbabilityTable
+    (every sample has its own k-mer coverage peak, src/commands.cpp:840-846).  Equal to one pg_hmm_run call per sample, bit for bit,
+    and to the oracle."""
+    rng = np.random.default_rng(4300 + n_paths)
+    base = [random_panel(rng, n, n_paths, max_alleles=3, undefined_frac=0.03, kmers_per_allele=(0, 8)) for n in (400, 130)]
+    peaks = [12, 30, 21]
+    tables = [pg.ProbabilityTable(pk // 4, pk * 4, 2 * pk, 0.01) for pk in peaks]
+    counts, covs = [], []
+    for pk in peaks:
+        counts.append([rng.integers(0, 2 * pk, size=len(p.kmer_counts)).astype(np.uint16) for p in base])
+        covs.append([rng.integers(max(pk // 2, 1), 2 * pk, size=p.n_variants).astype(np.uint16) for p in base])
+    kw = dict(recombrate=1.26, effective_N=1e-5)
+    batched = engine.hmm_run_samples(base, counts, covs, tables, **kw)
+    for s_, pk in enumerate(peaks):
+        ps = [copy.deepcopy(p) for p in base]
+        for p, c_, v_ in zip(ps, counts[s_], covs[s_]):
+            p.kmer_counts[:] = c_
+            p.coverage[:] = v_
+        alone = engine.hmm_run(ps, tables[s_], **kw)
+        want = oracles.cpu_hmm_run(oracle, "pgo_", ps, tables[s_], **kw)
+        for a, b, w in zip(alone, batched[s_], want):
+            assert np.array_equal(a.likelihoods, b.likelihoods) and np.array_equal(a.genotype, b.genotype) and np.array_equal(a.quality, b.quality)
+            assert np.array_equal(a.coverage, b.coverage)
+            assert_results_close(b, w, atol=1e-300, label=f"samples P={n_paths} peak={pk}")
