@@ -178,3 +178,48 @@ def test_device_selection_large_bubble_uses_the_global_scratch():
     got = pg.UniqueKmerSelection(counts, flat).panel()
     assert_same_panel(got, want)
     assert int(want.kmer_offsets[1]) == 301                    # max(301, P) k-mers, round-robin over the alleles
+
+
+def test_closed_form_of_the_round_robin_equals_the_reference_loop():
+    """`select_kmers` lets the alleles take turns (src/stepwiseuniquekmercomputer.cpp:74-92).  The kernel's single-thread walk uses the
+    closed form "rounds taken completely + the first alleles of the cut round" (csrc/index_build.cu); this mirrors both in Python
+    over random queue lengths, caps and totals (round boundaries that hit the total exactly included)."""
+    import random
+
+    def reference(q, max_kmers, max_total):
+        taken, left, n, keep = {a: 0 for a in q}, dict(q), 0, True
+        while n < max_total and keep:
+            added = False
+            for a in sorted(q):
+                if left[a] > 0 and taken[a] < max_kmers:
+                    taken[a] += 1; left[a] -= 1; added = True; n += 1
+                if n >= max_total:
+                    break
+            keep = added
+        return taken
+
+    def closed_form(q, max_kmers, max_total):
+        rounds = [0] * 33
+        for a in q:
+            for j in range(min(q[a], max_kmers)):
+                rounds[j] += 1
+        full = taken_n = 0
+        while full < max_kmers and rounds[full] > 0 and taken_n + rounds[full] <= max_total:
+            taken_n += rounds[full]; full += 1
+        extra = max_total - taken_n if (full < max_kmers and taken_n < max_total) else 0
+        if full < max_kmers:
+            extra = min(extra, rounds[full])
+        taken = {a: 0 for a in q}
+        for a in sorted(q):
+            for j in range(q[a]):
+                take = j < full
+                if not take and j == full and extra > 0:
+                    take, extra = True, extra - 1
+                taken[a] += int(take)
+        return taken
+
+    rnd = random.Random(7)
+    for _ in range(20000):
+        q = {a: rnd.choice([1, 2, 3, 5, 16, 17, 31, 32, 33, 40]) for a in rnd.sample(range(50), rnd.randint(1, 12))}
+        mk, mt = rnd.choice([16, 32, 3, 1]), rnd.choice([301, 5, 17, 40, 64, 33])
+        assert reference(q, mk, mt) == closed_form(q, mk, mt), (q, mk, mt)
