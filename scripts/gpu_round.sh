@@ -21,7 +21,8 @@ bench_hmm)
   timeout 1200 python scripts/bench_hmm.py > $out/bench_hmm_$tag.jsonl 2> $out/bench_hmm_$tag.err; cat $out/bench_hmm_$tag.jsonl; tail -3 $out/bench_hmm_$tag.err;;
 launches)
   # every launch of one step of the default workload with its device time (cold-cache, serialised: shares, not absolutes)
-  PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_$tag.csv \
+  # (ncu writes its log at exit: bound the number of profiled launches and the wall time, or a budget-clamped call loses everything)
+  PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout ${LAUNCH_TIMEOUT:-600} ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-1500} --csv --log-file $out/launches_$tag.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload ${WL:-cfg3s} > $out/launches_$tag.out 2>&1; tail -3 $out/launches_$tag.out;;
 ncu)
   PG_BENCH_MIN_WARMUP=1 PG_BENCH_E2E_STEPS=0 timeout 1500 ncu --set full --clock-control none --import-source on \
